@@ -1,0 +1,152 @@
+/* lsp_b200.h -- C ABI of the B200-native proving backend for the Plonky3
+ * prover loop that distributed-lab/linea-stark-prover drives on its Linea
+ * permutation AIR.
+ *
+ * The reference has no FFI of its own: its backend-selection point is the set
+ * of type aliases in reference `bin/src/config.rs:9-25` and the single
+ * `prove(..)` call at `bin/src/main.rs:80-86`.  Each entry point below names
+ * the Plonky3 trait method (as instantiated by those aliases) that a Rust
+ * `extern "C"` shim would forward to it; INTEGRATION.md shows the shim.
+ *
+ * Conventions
+ *  - Field elements are BLS12-377 Fr in the host type's own memory format:
+ *    4 x uint64_t little-endian limbs of the Montgomery representative
+ *    (a * 2^256 mod r), fully reduced (`Bls12_377Fr`, `trace/src/permutation.rs:102`).
+ *  - Host matrices are row-major (`RowMajorMatrix<Val>`, `trace/src/lib.rs:94-106`).
+ *  - Every function returns 0 on success or a negative LSP_ERR_* code; nothing
+ *    throws or aborts across the boundary.  `lsp_last_error` gives the text.
+ *  - One `lsp_ctx` per host thread; calls on a ctx are serialised on its stream.
+ *  - There is no CPU fallback: without a CUDA device `lsp_ctx_create` fails.
+ */
+#ifndef LSP_B200_H
+#define LSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSP_OK 0
+#define LSP_ERR_PARAM (-1)   /* bad argument / unsupported shape            */
+#define LSP_ERR_CUDA (-2)    /* CUDA runtime error, see lsp_last_error      */
+#define LSP_ERR_STATE (-3)   /* call order (e.g. Poseidon2 constants unset) */
+#define LSP_ERR_NOMEM (-4)
+#define LSP_ERR_COMM (-5)    /* NCCL / multi-GPU plumbing                   */
+
+#define LSP_ABI_VERSION 1
+
+typedef struct lsp_ctx lsp_ctx;
+typedef struct lsp_mat lsp_mat;               /* device-resident matrix of Fr            */
+typedef struct lsp_tree lsp_tree;             /* MerkleTreeMmcs::ProverData              */
+typedef struct lsp_challenger lsp_challenger; /* device-resident HashChallenger<Val,Hash,1> */
+
+/* ---- context ----------------------------------------------------------- */
+int lsp_abi_version(void);
+int lsp_ctx_create(int device, lsp_ctx** out);
+void lsp_ctx_destroy(lsp_ctx* ctx);
+const char* lsp_last_error(const lsp_ctx* ctx);
+int lsp_ctx_sync(lsp_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
+uint64_t lsp_kernel_launches(const lsp_ctx* ctx);
+
+/* `Perm::new_from_rng(8, 22, &mut rng)` (bin/src/main.rs:49): the host draws the
+ * constants and hands them over.  `constants` holds, in draw order,
+ * rounds_f/2 x 3 initial external, rounds_f/2 x 3 terminal external, then
+ * rounds_p internal constants; `internal_diag_m1` the 3 diagonal entries
+ * (matrix = diag + all-ones).  sbox_d in {3,5,7,11,17}. */
+int lsp_set_poseidon2(lsp_ctx* ctx, int width, int sbox_d, int rounds_f, int rounds_p,
+                      const uint64_t* constants, const uint64_t* internal_diag_m1);
+
+/* ---- parity probes (SURVEY.md section 4 tier 3) --------------------------- */
+/* Elementwise Fr ops on host arrays: op 0 add, 1 sub, 2 mul, 3 inverse (b unused),
+ * 4 halve (b unused).  Replaces ark-ff `Fp256` arithmetic behind `Val` (bin/src/config.rs:9). */
+int lsp_fr_op(lsp_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n);
+/* `Permutation::permute` of `Perm` on n independent [Fr;3] states. */
+int lsp_poseidon2_permute(lsp_ctx* ctx, const uint64_t* states_in, uint64_t* states_out, size_t n);
+/* `CryptographicHasher::hash_iter` of `Hash` (bin/src/config.rs:12) on each of
+ * `rows` rows of a host row-major matrix. */
+int lsp_hash_rows(lsp_ctx* ctx, const uint64_t* rowmajor, size_t rows, size_t width, uint64_t* digests_out);
+
+/* ---- matrices ---------------------------------------------------------- */
+int lsp_mat_upload(lsp_ctx* ctx, const uint64_t* rowmajor, size_t rows, size_t width, lsp_mat** out);
+int lsp_mat_download(lsp_ctx* ctx, const lsp_mat* m, uint64_t* rowmajor_out);
+int lsp_mat_download_rows(lsp_ctx* ctx, const lsp_mat* m, size_t row0, size_t nrows, uint64_t* rowmajor_out);
+size_t lsp_mat_rows(const lsp_mat* m);
+size_t lsp_mat_width(const lsp_mat* m);
+void lsp_mat_free(lsp_ctx* ctx, lsp_mat* m);
+
+/* ---- TwoAdicSubgroupDft<Val> for `Dft` (bin/src/config.rs:22) -------------- */
+/* `coset_lde_batch(mat, added_bits, shift)`: out has rows << added_bits rows and
+ * holds, at row bitrev(j), the values p_col(shift * omega^j) -- i.e. the storage of
+ * `.bit_reverse_rows().to_row_major_matrix()` that TwoAdicFriPcs::commit consumes.
+ * `in` is not consumed.  If `coeffs_out` is non-NULL it receives the N x W
+ * coefficient matrix of the interpolants (kept by the PCS for openings). */
+int lsp_coset_lde_batch(lsp_ctx* ctx, const lsp_mat* in, int added_bits, const uint64_t shift[4],
+                        lsp_mat** out_bitrev, lsp_mat** coeffs_out);
+
+/* ---- Mmcs<Val> for `ValMmcs` / `ChallengeMmcs` (bin/src/config.rs:19-20) --- */
+/* `commit(Vec<M>)`: all matrices must share one height (the only case on the
+ * reference's path).  The tree borrows the matrices; they must outlive it. */
+int lsp_merkle_commit(lsp_ctx* ctx, const lsp_mat* const* mats, int n_mats, uint64_t root_out[4], lsp_tree** out);
+/* `open_batch(index, &prover_data)`: rows_out receives the opened row of every
+ * matrix back to back (sum of widths elements), siblings_out log2(height) digests. */
+int lsp_merkle_open_batch(lsp_ctx* ctx, const lsp_tree* t, size_t index, uint64_t* rows_out, uint64_t* siblings_out);
+/* One digest layer (0 = leaf digests), for parity tests. */
+int lsp_merkle_layer(lsp_ctx* ctx, const lsp_tree* t, int layer, uint64_t* digests_out);
+size_t lsp_merkle_height(const lsp_tree* t);
+void lsp_tree_free(lsp_ctx* ctx, lsp_tree* t);
+
+/* ---- AIR config: `AirPermutationConfig` (air/src/air_permutation.rs:2-7) ---- */
+typedef struct {
+    uint32_t n_cols;         /* a_columns_ids.len() == b_columns_ids.len() */
+    const uint32_t* a_ids;   /* a_columns_ids */
+    const uint32_t* b_ids;   /* b_columns_ids */
+    uint32_t b_inverse_id;
+    uint32_t check_id;
+} lsp_perm_air_cfg;
+
+/* `quotient_values` of p3-uni-stark with `LineaAIR::eval` -> `eval_permutation`
+ * (air/src/lib.rs:47-54,116-167) folded by powers of `alpha`, times 1/Z_H.
+ * `lde_bitrev` is the committed trace LDE; the first N<<log_q rows are read.
+ * Output: q = 1<<log_q chunk matrices (N x 1, natural order), chunk c = rows
+ * c, c+q, ... of the quotient vector (`split_evals`). */
+int lsp_quotient_permutation(lsp_ctx* ctx, const lsp_mat* lde_bitrev, int log_n, int log_q,
+                             const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                             const uint64_t alpha[4], lsp_mat** chunks_out);
+
+/* ---- FRI pieces of `TwoAdicFriPcs` (bin/src/config.rs:24-25) -------------- */
+/* `fold_matrix(beta, m)`: in = vector of 2h elements viewed as h rows of 2; out h elements. */
+int lsp_fri_fold(lsp_ctx* ctx, const lsp_mat* in, const uint64_t beta[4], lsp_mat** out);
+
+/* ---- `prove` (bin/src/main.rs:80-86) ------------------------------------- */
+typedef struct {
+    uint32_t log_blowup;          /* FriConfig.log_blowup        (main.rs:59) */
+    uint32_t log_final_poly_len;  /* FriConfig.log_final_poly_len (main.rs:60) */
+    uint32_t num_queries;         /* FriConfig.num_queries        (main.rs:61) */
+    uint32_t proof_of_work_bits;  /* FriConfig.proof_of_work_bits (main.rs:62) */
+} lsp_fri_config;
+
+/* Number of uint64_t words `lsp_prove_permutation` writes for this shape. */
+size_t lsp_proof_words(uint32_t log_n, uint32_t width, uint32_t log_q, const lsp_fri_config* fri);
+
+/* Full uni-STARK prove of the permutation AIR, device-resident end to end
+ * (commit trace, quotient, commit quotient, open, FRI), transcript included
+ * (`HashChallenger<Val,Hash,1>` with empty initial state, main.rs:78).
+ * `trace` is a host row-major N x W matrix.  The proof is written as a flat
+ * array of Fr (Montgomery limbs) in the order documented in DESIGN.md
+ * ("proof layout"); `timings_ms_out` (optional, 8 floats) receives per-stage
+ * CUDA-event times named after the reference's tracing spans. */
+int lsp_prove_permutation(lsp_ctx* ctx, const lsp_fri_config* fri, const uint64_t* trace, size_t rows,
+                          size_t width, const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                          uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+/* Same, for a trace already uploaded with lsp_mat_upload (bench "value" leg). */
+int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp_mat* trace,
+                              const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                              uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LSP_B200_H */

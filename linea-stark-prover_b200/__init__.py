@@ -1,0 +1,10 @@
+"""linea-stark-prover_b200: B200-native (sm_100a) proving backend for the Plonky3
+prover loop of distributed-lab/linea-stark-prover (permutation AIR over BLS12-377 Fr).
+
+The directory name carries a hyphen (it mirrors the reference's repo name), so
+it is imported under the module name `linea_stark_prover_b200` via
+`__graft_entry__.load_package()`.
+"""
+from . import ffi  # noqa: F401
+from .backend import (AirPermutationConfig, BackendError, Context, FriConfig, GpuDft, GpuMmcs, Mat, Proof, Tree,  # noqa: F401
+                      fri_fold, from_mont_array, prove, quotient_permutation, to_mont_array)

@@ -1,0 +1,377 @@
+"""Host-side mirror of the Plonky3 trait surface the reference selects in
+`bin/src/config.rs:9-25`, implemented on the C ABI of liblsp_b200.so.
+
+    Context                  <- construction done in bin/src/main.rs:49-66
+    GpuDft.coset_lde_batch   <- TwoAdicSubgroupDft::coset_lde_batch   (Dft, config.rs:22)
+    GpuMmcs.commit/open_batch<- Mmcs::commit / open_batch             (ValMmcs, config.rs:19)
+    Context.permute/hash_iter<- Permutation::permute / CryptographicHasher::hash_iter
+    prove                    <- p3_uni_stark::prove                   (main.rs:80-86)
+
+Same names, argument meaning and error behaviour (the prover side of Plonky3
+panics on misuse: here a `BackendError`).  Values cross as Python ints in
+canonical form; the wire format underneath is Montgomery limbs (see ffi.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import ffi
+
+R_MOD = 8444461749428370424248824938781546531375899335154063827935233455917409239041
+_MONT_R = (1 << 256) % R_MOD
+_MONT_RINV = pow(_MONT_R, -1, R_MOD)
+
+
+class BackendError(RuntimeError):
+    pass
+
+
+def to_mont_array(values) -> np.ndarray:
+    """ints (canonical) -> uint64[n,4] Montgomery limbs."""
+    buf = bytearray()
+    for v in values:
+        buf += ((int(v) % R_MOD) * _MONT_R % R_MOD).to_bytes(32, "little")
+    return np.frombuffer(bytes(buf), dtype=np.uint64).reshape(-1, 4).copy()
+
+
+def from_mont_array(a: np.ndarray) -> list:
+    raw = np.ascontiguousarray(a, dtype=np.uint64).tobytes()
+    return [int.from_bytes(raw[i:i + 32], "little") * _MONT_RINV % R_MOD for i in range(0, len(raw), 32)]
+
+
+class Context:
+    """One CUDA device + stream + Poseidon2 parameters (lsp_ctx)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = ffi.load()
+        h = C.c_void_p()
+        rc = self.lib.lsp_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise BackendError(f"lsp_ctx_create(device={device}) failed with {rc}: no usable CUDA device "
+                               "(this backend has no CPU fallback)")
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lsp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.lsp_last_error(self.h)
+            raise BackendError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def sync(self):
+        self.check(self.lib.lsp_ctx_sync(self.h), "lsp_ctx_sync")
+
+    def kernel_launches(self) -> int:
+        return int(self.lib.lsp_kernel_launches(self.h))
+
+    # -- Perm::new_from_rng constants handed over (bin/src/main.rs:49) --------
+    def set_poseidon2(self, sbox_d, rounds_f, rounds_p, flat_constants, diag_m1=(1, 1, 2)):
+        c = to_mont_array(flat_constants)
+        d = to_mont_array(diag_m1)
+        self.check(self.lib.lsp_set_poseidon2(self.h, 3, sbox_d, rounds_f, rounds_p, ffi.as_u64p(c), ffi.as_u64p(d)),
+                   "lsp_set_poseidon2")
+
+    # -- parity probes ----------------------------------------------------------
+    def fr_op(self, op: str, a, b=None):
+        code = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "halve": 4}[op]
+        aa = to_mont_array(a)
+        bb = to_mont_array(b) if b is not None else aa
+        out = np.empty_like(aa)
+        self.check(self.lib.lsp_fr_op(self.h, code, ffi.as_u64p(aa), ffi.as_u64p(bb), ffi.as_u64p(out), len(aa)),
+                   "lsp_fr_op")
+        return from_mont_array(out)
+
+    def permute(self, states):
+        """`Perm::permute` on a list of [Fr;3] states."""
+        flat = [x for s in states for x in s]
+        a = to_mont_array(flat)
+        out = np.empty_like(a)
+        self.check(self.lib.lsp_poseidon2_permute(self.h, ffi.as_u64p(a), ffi.as_u64p(out), len(states)),
+                   "lsp_poseidon2_permute")
+        o = from_mont_array(out)
+        return [o[3 * i:3 * i + 3] for i in range(len(states))]
+
+    def hash_rows(self, rows):
+        """`Hash::hash_iter` applied to every row of a row-major matrix."""
+        n, w = len(rows), len(rows[0]) if rows else 0
+        a = to_mont_array([x for r in rows for x in r]) if w else np.zeros((0, 4), dtype=np.uint64)
+        out = np.empty((n, 4), dtype=np.uint64)
+        src = a if w else np.zeros((1, 4), dtype=np.uint64)
+        self.check(self.lib.lsp_hash_rows(self.h, ffi.as_u64p(src), n, w, ffi.as_u64p(out)), "lsp_hash_rows")
+        return from_mont_array(out)
+
+    # -- matrices ---------------------------------------------------------------
+    def upload(self, rows) -> "Mat":
+        n, w = len(rows), len(rows[0])
+        a = to_mont_array([x for r in rows for x in r])
+        return self.upload_array(a, n, w)
+
+    def upload_array(self, limbs: np.ndarray, n: int, w: int) -> "Mat":
+        h = C.c_void_p()
+        self.check(self.lib.lsp_mat_upload(self.h, ffi.as_u64p(limbs), n, w, C.byref(h)), "lsp_mat_upload")
+        return Mat(self, h)
+
+
+class Mat:
+    """Device-resident matrix (lsp_mat).  `rows()` returns canonical ints, row-major."""
+
+    def __init__(self, ctx: Context, h):
+        self.ctx, self.h = ctx, h
+
+    @property
+    def height(self):
+        return int(self.ctx.lib.lsp_mat_rows(self.h))
+
+    @property
+    def width(self):
+        return int(self.ctx.lib.lsp_mat_width(self.h))
+
+    def download_array(self, row0=0, nrows=None) -> np.ndarray:
+        nrows = self.height - row0 if nrows is None else nrows
+        out = np.empty((nrows * self.width, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.lsp_mat_download_rows(self.ctx.h, self.h, row0, nrows, ffi.as_u64p(out)),
+                       "lsp_mat_download_rows")
+        return out
+
+    def rows(self, row0=0, nrows=None):
+        w = self.width
+        flat = from_mont_array(self.download_array(row0, nrows))
+        return [flat[i:i + w] for i in range(0, len(flat), w)]
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.lsp_mat_free(self.ctx.h, self.h)
+            self.h = None
+
+
+class GpuDft:
+    """`Dft` (bin/src/config.rs:22) -- only `coset_lde_batch` is on the prover path."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def coset_lde_batch(self, mat: Mat, added_bits: int, shift: int, want_coeffs: bool = False):
+        """Returns the L x W matrix in bit-reversed row order (the storage
+        `.bit_reverse_rows().to_row_major_matrix()` yields)."""
+        out, co = C.c_void_p(), C.c_void_p()
+        s = to_mont_array([shift])
+        self.ctx.check(self.ctx.lib.lsp_coset_lde_batch(self.ctx.h, mat.h, added_bits, ffi.as_u64p(s), C.byref(out),
+                                                        C.byref(co) if want_coeffs else None), "lsp_coset_lde_batch")
+        if want_coeffs:
+            return Mat(self.ctx, out), Mat(self.ctx, co)
+        return Mat(self.ctx, out)
+
+
+class Tree:
+    def __init__(self, ctx: Context, h, mats):
+        self.ctx, self.h, self.mats = ctx, h, mats  # keep matrices alive: the tree borrows them
+
+    @property
+    def height(self):
+        return int(self.ctx.lib.lsp_merkle_height(self.h))
+
+    def layer(self, k: int):
+        n = self.height >> k
+        out = np.empty((n, 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.lsp_merkle_layer(self.ctx.h, self.h, k, ffi.as_u64p(out)), "lsp_merkle_layer")
+        return from_mont_array(out)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.lsp_tree_free(self.ctx.h, self.h)
+            self.h = None
+
+
+class GpuMmcs:
+    """`ValMmcs` / `ChallengeMmcs` (bin/src/config.rs:19-20)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+
+    def commit(self, mats):
+        arr = (C.c_void_p * len(mats))(*[m.h for m in mats])
+        root = np.empty((1, 4), dtype=np.uint64)
+        h = C.c_void_p()
+        self.ctx.check(self.ctx.lib.lsp_merkle_commit(self.ctx.h, arr, len(mats), ffi.as_u64p(root), C.byref(h)),
+                       "lsp_merkle_commit")
+        return from_mont_array(root)[0], Tree(self.ctx, h, list(mats))
+
+    def open_batch(self, index: int, tree: Tree):
+        widths = [m.width for m in tree.mats]
+        tw = sum(widths)
+        log_h = tree.height.bit_length() - 1
+        rows = np.empty((tw, 4), dtype=np.uint64)
+        sib = np.empty((max(log_h, 1), 4), dtype=np.uint64)
+        self.ctx.check(self.ctx.lib.lsp_merkle_open_batch(self.ctx.h, tree.h, index, ffi.as_u64p(rows), ffi.as_u64p(sib)),
+                       "lsp_merkle_open_batch")
+        flat = from_mont_array(rows)
+        opened, o = [], 0
+        for w in widths:
+            opened.append(flat[o:o + w])
+            o += w
+        return opened, from_mont_array(sib)[:log_h]
+
+
+# ---------------------------------------------------------------------------
+# AIR config + prove (bin/src/main.rs:58-86)
+# ---------------------------------------------------------------------------
+class AirPermutationConfig:
+    """`AirPermutationConfig` (air/src/air_permutation.rs:2-23)."""
+
+    def __init__(self, a_columns_ids, b_columns_ids, b_inverse_id, check_id):
+        self.a_columns_ids = list(a_columns_ids)
+        self.b_columns_ids = list(b_columns_ids)
+        self.b_inverse_id = int(b_inverse_id)
+        self.check_id = int(check_id)
+
+    def width(self):
+        return len(self.a_columns_ids) + len(self.b_columns_ids) + 2
+
+
+class FriConfig:
+    """`FriConfig` literals of bin/src/main.rs:58-64."""
+
+    def __init__(self, log_blowup=3, log_final_poly_len=0, num_queries=33, proof_of_work_bits=0):
+        self.log_blowup, self.log_final_poly_len = log_blowup, log_final_poly_len
+        self.num_queries, self.proof_of_work_bits = num_queries, proof_of_work_bits
+
+    def c_struct(self):
+        return ffi.FriConfig(self.log_blowup, self.log_final_poly_len, self.num_queries, self.proof_of_work_bits)
+
+
+def _c_cfgs(cfgs):
+    keep = []
+    arr = (ffi.PermAirCfg * len(cfgs))()
+    for i, c in enumerate(cfgs):
+        if len(c.a_columns_ids) != len(c.b_columns_ids):
+            raise BackendError("a and b must have the same number of columns")
+        a = (C.c_uint32 * len(c.a_columns_ids))(*c.a_columns_ids)
+        b = (C.c_uint32 * len(c.b_columns_ids))(*c.b_columns_ids)
+        keep += [a, b]
+        arr[i] = ffi.PermAirCfg(len(c.a_columns_ids), a, b, c.b_inverse_id, c.check_id)
+    return arr, keep
+
+
+STAGE_NAMES = ["commit_trace_lde", "commit_trace_merkle", "quotient", "commit_quotient", "open_reduce",
+               "fri_commit_phase", "grind_query", "d2h"]
+
+
+class Proof:
+    """Flat proof buffer (layout in host/prover.cu) with a structured view."""
+
+    def __init__(self, words: np.ndarray, log_n: int, width: int, log_q: int, fri: FriConfig):
+        self.words, self.log_n, self.width, self.log_q, self.fri = words, log_n, width, log_q, fri
+
+    def to_dict(self):
+        """Same shape as the reference's `Proof` struct, canonical ints."""
+        w, q = self.width, 1 << self.log_q
+        log_l = self.log_n + self.fri.log_blowup
+        rounds = self.log_n - self.fri.log_final_poly_len
+        f = 1 << (self.fri.log_blowup + self.fri.log_final_poly_len)
+        raw = self.words.reshape(-1, 4)
+        vals = from_mont_array(raw)
+        pos = 0
+
+        def take(k):
+            nonlocal pos
+            out = vals[pos:pos + k]
+            pos += k
+            return out
+
+        trace_commit, quot_commit = take(2)
+        local, nxt = take(w), take(w)
+        chunks = [[x] for x in take(q)]
+        commits = take(rounds)
+        final_poly = take(f)
+        pow_witness = take(1)[0]
+        queries, indices = [], []
+        for _ in range(self.fri.num_queries):
+            indices.append(int(raw[pos][0]))
+            pos += 1
+            ip = []
+            row = take(w)
+            ip.append(dict(opened_values=[row], opening_proof=take(log_l)))
+            row = take(q)
+            ip.append(dict(opened_values=[[x] for x in row], opening_proof=take(log_l)))
+            steps = []
+            for r in range(rounds):
+                sib = take(1)[0]
+                steps.append(dict(sibling_value=sib, opening_proof=take(log_l - 1 - r)))
+            queries.append(dict(input_proof=ip, commit_phase_openings=steps))
+        assert pos == len(vals)
+        d = dict(commitments=dict(trace=trace_commit, quotient_chunks=quot_commit),
+                 opened_values=dict(trace_local=local, trace_next=nxt, quotient_chunks=chunks),
+                 opening_proof=dict(commit_phase_commits=commits, query_proofs=queries, final_poly=final_poly,
+                                    pow_witness=pow_witness),
+                 degree_bits=self.log_n)
+        return d, indices
+
+
+def prove(ctx: Context, fri: FriConfig, cfgs, trace, publics, timings=None):
+    """`prove(&config, &air, &mut challenger, trace, &publics)` (bin/src/main.rs:80-86).
+
+    `trace`: row-major list of rows (canonical ints), a uint64[n*w,4] limb array
+    with `trace_shape=(n,w)` given via a tuple (array, n, w), or a device `Mat`."""
+    cf = fri.c_struct()
+    arr, keep = _c_cfgs(cfgs)
+    pub = to_mont_array(publics)
+    assert pub.shape == (2, 4)
+    tm = np.zeros(8, dtype=np.float32)
+    width = sum(c.width() for c in cfgs)
+    if isinstance(trace, Mat):
+        n, w = trace.height, trace.width
+    elif isinstance(trace, tuple):
+        limbs, n, w = trace
+    else:
+        n, w = len(trace), len(trace[0])
+        limbs = to_mont_array([x for r in trace for x in r])
+    if n & (n - 1) or n == 0:
+        raise BackendError(f"trace height {n} is not a power of two")
+    log_n = n.bit_length() - 1
+    log_q = 1
+    words = int(ctx.lib.lsp_proof_words(log_n, w, log_q, C.byref(cf)))
+    if words == 0:
+        raise BackendError("unsupported FRI parameters for this trace height")
+    out = np.empty(words, dtype=np.uint64)
+    if isinstance(trace, Mat):
+        rc = ctx.lib.lsp_prove_permutation_dev(ctx.h, C.byref(cf), trace.h, arr, len(cfgs), ffi.as_u64p(pub),
+                                               ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    else:
+        rc = ctx.lib.lsp_prove_permutation(ctx.h, C.byref(cf), ffi.as_u64p(limbs), n, w, arr, len(cfgs),
+                                           ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    ctx.check(rc, "lsp_prove_permutation")
+    if timings is not None:
+        timings.update({k: float(v) for k, v in zip(STAGE_NAMES, tm)})
+    del keep, width
+    return Proof(out, log_n, w, log_q, fri)
+
+
+def quotient_permutation(ctx: Context, lde: Mat, log_n: int, log_q: int, cfgs, publics, alpha) -> Mat:
+    """`quotient_values` + `split_evals`: returns the N x q matrix whose column c is chunk c."""
+    arr, keep = _c_cfgs(cfgs)
+    pub = to_mont_array(publics)
+    al = to_mont_array([alpha])
+    h = C.c_void_p()
+    ctx.check(ctx.lib.lsp_quotient_permutation(ctx.h, lde.h, log_n, log_q, arr, len(cfgs), ffi.as_u64p(pub),
+                                               ffi.as_u64p(al), C.byref(h)), "lsp_quotient_permutation")
+    del keep
+    return Mat(ctx, h)
+
+
+def fri_fold(ctx: Context, vec: Mat, beta: int) -> Mat:
+    """`fold_matrix(beta, m)` on a device vector (len x 1) viewed as len/2 rows of 2."""
+    b = to_mont_array([beta])
+    h = C.c_void_p()
+    ctx.check(ctx.lib.lsp_fri_fold(ctx.h, vec.h, ffi.as_u64p(b), C.byref(h)), "lsp_fri_fold")
+    return Mat(ctx, h)

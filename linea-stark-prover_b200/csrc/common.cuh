@@ -1,0 +1,115 @@
+// Shared host-side declarations of the CUDA library (context, handles, launch helpers).
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/lsp_b200.h"
+#include "fr.cuh"
+#include "poseidon2.cuh"
+
+namespace lsp {
+struct TwiddleCache;
+}
+
+struct lsp_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool p2_set = false;
+    lsp::P2Params p2;
+    uint64_t launches = 0;
+    // omega_{2^k}^j tables, j < 2^(k-1), forward and inverse, keyed by k
+    std::map<int, lsp::Fr*> tw_fwd, tw_inv;
+    // pinned staging for small D2H reads
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+// Column-major ("planar") on the device: column c is the contiguous run
+// d[c*rows .. (c+1)*rows).  Host matrices are row-major; upload/download transpose.
+struct lsp_mat {
+    lsp::Fr* d = nullptr;
+    size_t rows = 0, width = 0;
+    bool owns = true;
+};
+
+struct lsp_tree {
+    lsp::Fr* digests = nullptr;  // layer k at offset 2h - (2h >> k), 2h-1 digests in total
+    size_t height = 0;
+    int log_h = 0;
+    std::vector<const lsp_mat*> mats;
+    size_t total_width = 0;
+    const lsp::Fr** d_cols = nullptr;  // device array of total_width column base pointers
+};
+
+namespace lsp {
+
+inline int set_err(lsp_ctx* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+
+#define LSP_CUDA(ctx, call)                                                                     \
+    do {                                                                                        \
+        cudaError_t e__ = (call);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return lsp::set_err(ctx, e__ == cudaErrorMemoryAllocation ? LSP_ERR_NOMEM : LSP_ERR_CUDA, \
+                                "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define LSP_TRY(call)            \
+    do {                         \
+        int rc__ = (call);       \
+        if (rc__ != LSP_OK) return rc__; \
+    } while (0)
+
+// Launch on the ctx stream, count it, and surface launch-time errors.
+#define LSP_LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+    do {                                                                     \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);     \
+        (ctx)->launches++;                                                   \
+        LSP_CUDA(ctx, cudaGetLastError());                                   \
+    } while (0)
+
+inline size_t tree_layer_offset(size_t h, int k) { return 2 * h - ((2 * h) >> k); }
+
+inline int dev_alloc(lsp_ctx* ctx, void** p, size_t bytes) {
+    LSP_CUDA(ctx, cudaMallocAsync(p, bytes ? bytes : 16, ctx->stream));
+    return LSP_OK;
+}
+inline void dev_free(lsp_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+
+inline int ilog2(size_t n) {
+    int k = 0;
+    while ((size_t(1) << k) < n) k++;
+    return k;
+}
+inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+
+// Grid size for a grid-stride kernel: enough CTAs to fill every SM several times over.
+inline unsigned grid_for(const lsp_ctx* ctx, size_t n, unsigned block, unsigned ctas_per_sm = 8) {
+    size_t need = (n + block - 1) / block;
+    size_t cap = size_t(ctx->sm_count) * ctas_per_sm;
+    if (need < 1) need = 1;
+    return unsigned(need < cap ? need : cap);
+}
+
+// ---- internal kernels' host entry points (defined in the .cu files) -------
+int mat_alloc(lsp_ctx* ctx, size_t rows, size_t width, lsp_mat** out);
+int twiddles(lsp_ctx* ctx, int log_n, bool inverse, const Fr** out);
+
+}  // namespace lsp

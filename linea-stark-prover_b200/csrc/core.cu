@@ -1,0 +1,436 @@
+// Context, matrices, field/permutation parity probes and the Merkle MMCS.
+#include "stark.cuh"
+
+using namespace lsp;
+
+// ---------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_fr_op(int op, const Fr* __restrict__ a, const Fr* __restrict__ b,
+                                               Fr* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        Fr x = fr_load(a + i), r;
+        switch (op) {
+            case 0: r = fr_add(x, fr_load(b + i)); break;
+            case 1: r = fr_sub(x, fr_load(b + i)); break;
+            case 2: r = fr_mul(x, fr_load(b + i)); break;
+            case 3: r = fr_inv(x); break;
+            default: r = fr_halve(x); break;
+        }
+        fr_store(out + i, r);
+    }
+}
+
+// host row-major (rows x width)  <->  device column-major
+__global__ void __launch_bounds__(256) k_rm_to_cm(const Fr* __restrict__ rm, Fr* __restrict__ cm, size_t rows,
+                                                  size_t width, size_t row0, size_t nrows) {
+    size_t total = nrows * width;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        size_t r = i / width, c = i - r * width;
+        fr_store(cm + c * rows + row0 + r, fr_load_nc(rm + i));
+    }
+}
+__global__ void __launch_bounds__(256) k_cm_to_rm(const Fr* __restrict__ cm, Fr* __restrict__ rm, size_t rows,
+                                                  size_t width, size_t row0, size_t nrows) {
+    size_t total = nrows * width;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        size_t r = i / width, c = i - r * width;
+        fr_store(rm + i, fr_load_nc(cm + c * rows + row0 + r));
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(128) k_p2_permute(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
+                                                    Fr* __restrict__ out, size_t n) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        Fr s0 = fr_load(in + 3 * i), s1 = fr_load(in + 3 * i + 1), s2 = fr_load(in + 3 * i + 2);
+        p2_permute<D>(P, s0, s1, s2);
+        fr_store(out + 3 * i, s0);
+        fr_store(out + 3 * i + 1, s1);
+        fr_store(out + 3 * i + 2, s2);
+    }
+}
+
+// Leaf digests: one thread per row.  PaddingFreeSponge<Perm,3,2,1>::hash_iter over
+// the concatenation of that row in every matrix (overwrite mode, rate 2).
+// cols[] are column base pointers (column-major storage => coalesced across rows).
+template <int D>
+__global__ void __launch_bounds__(128) k_leaf_hash(const __grid_constant__ P2Params P, const Fr* const* __restrict__ cols,
+                                                   int width, size_t rows, Fr* __restrict__ digests) {
+    for (size_t r = blockIdx.x * size_t(blockDim.x) + threadIdx.x; r < rows; r += size_t(gridDim.x) * blockDim.x) {
+        Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
+        int c = 0;
+        for (; c + 1 < width; c += 2) {
+            s0 = fr_load_nc(cols[c] + r);
+            s1 = fr_load_nc(cols[c + 1] + r);
+            p2_permute<D>(P, s0, s1, s2);
+        }
+        if (c < width) {  // odd tail: state[1] keeps its stale value
+            s0 = fr_load_nc(cols[c] + r);
+            p2_permute<D>(P, s0, s1, s2);
+        }
+        fr_store(digests + r, s0);
+    }
+}
+
+// One Merkle layer: out[i] = compress(in[2i], in[2i+1]).
+template <int D>
+__global__ void __launch_bounds__(128) k_compress_layer(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
+                                                        Fr* __restrict__ out, size_t n_out) {
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n_out; i += size_t(gridDim.x) * blockDim.x) {
+        Fr l = fr_load(in + 2 * i), r = fr_load(in + 2 * i + 1);
+        fr_store(out + i, p2_compress<D>(P, l, r));
+    }
+}
+
+// Gather one row across columns (open_batch) into a contiguous buffer.
+__global__ void k_gather_row(const Fr* const* __restrict__ cols, int width, size_t row, Fr* __restrict__ out) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < width) fr_store(out + c, fr_load(cols[c] + row));
+}
+__global__ void k_gather_siblings(const Fr* __restrict__ digests, size_t h, int log_h, size_t index, Fr* __restrict__ out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < log_h) {
+        size_t off = 2 * h - ((2 * h) >> k);
+        fr_store(out + k, fr_load(digests + off + ((index >> k) ^ 1)));
+    }
+}
+
+// ---------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------
+extern "C" int lsp_abi_version(void) { return LSP_ABI_VERSION; }
+
+extern "C" int lsp_ctx_create(int device, lsp_ctx** out) {
+    if (!out) return LSP_ERR_PARAM;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || device < 0 || device >= n) return LSP_ERR_CUDA;
+    lsp_ctx* ctx = new lsp_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return LSP_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+    // keep freed blocks in the stream-ordered pool: prove() allocates the same shapes every call
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    ctx->pinned_bytes = 1 << 20;
+    if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return LSP_ERR_NOMEM;
+    }
+    *out = ctx;
+    return LSP_OK;
+}
+
+extern "C" void lsp_ctx_destroy(lsp_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->tw_fwd) cudaFree(kv.second);
+    for (auto& kv : ctx->tw_inv) cudaFree(kv.second);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* lsp_last_error(const lsp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null ctx"; }
+
+extern "C" int lsp_ctx_sync(lsp_ctx* ctx) {
+    if (!ctx) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSP_OK;
+}
+
+extern "C" uint64_t lsp_kernel_launches(const lsp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+static bool limbs_reduced(const uint64_t* l) {
+    static const uint64_t P[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
+    for (int i = 3; i >= 0; i--) {
+        if (l[i] < P[i]) return true;
+        if (l[i] > P[i]) return false;
+    }
+    return false;
+}
+
+extern "C" int lsp_set_poseidon2(lsp_ctx* ctx, int width, int sbox_d, int rounds_f, int rounds_p,
+                                 const uint64_t* constants, const uint64_t* internal_diag_m1) {
+    if (!ctx || !constants || !internal_diag_m1) return LSP_ERR_PARAM;
+    if (width != 3) return set_err(ctx, LSP_ERR_PARAM, "only width 3 (Poseidon2Bls12337<3>) is supported, got %d", width);
+    if (!(sbox_d == 3 || sbox_d == 5 || sbox_d == 7 || sbox_d == 11 || sbox_d == 17))
+        return set_err(ctx, LSP_ERR_PARAM, "unsupported S-box degree %d", sbox_d);
+    if (rounds_f <= 0 || (rounds_f & 1) || rounds_f / 2 > P2_MAX_HALF_F || rounds_p < 0 || rounds_p > P2_MAX_P)
+        return set_err(ctx, LSP_ERR_PARAM, "unsupported round counts %d/%d", rounds_f, rounds_p);
+    int n_const = rounds_f * 3 + rounds_p;
+    for (int i = 0; i < n_const; i++)
+        if (!limbs_reduced(constants + 4 * i)) return set_err(ctx, LSP_ERR_PARAM, "round constant %d is not reduced", i);
+    for (int i = 0; i < 3; i++)
+        if (!limbs_reduced(internal_diag_m1 + 4 * i)) return set_err(ctx, LSP_ERR_PARAM, "diag %d is not reduced", i);
+    P2Params& p = ctx->p2;
+    memset(&p, 0, sizeof p);
+    p.half_f = rounds_f / 2;
+    p.rounds_p = rounds_p;
+    p.sbox_d = sbox_d;
+    const uint64_t* c = constants;
+    for (int r = 0; r < p.half_f; r++)
+        for (int i = 0; i < 3; i++, c += 4) memcpy(&p.ext_initial[r][i], c, 32);
+    for (int r = 0; r < p.half_f; r++)
+        for (int i = 0; i < 3; i++, c += 4) memcpy(&p.ext_terminal[r][i], c, 32);
+    for (int r = 0; r < rounds_p; r++, c += 4) memcpy(&p.internal[r], c, 32);
+    memcpy(p.diag_m1, internal_diag_m1, 96);
+    // diag (1,1,2) in Montgomery form -> add-only internal layer
+    static const uint64_t ONE[4] = {0x7d1c7ffffffffff3ull, 0x7257f50f6ffffff2ull, 0x16d81575512c0feeull, 0x0d4bda322bbb9a9dull};
+    static const uint64_t TWO[4] = {0xf0277fffffffffe5ull, 0x8b0573200fffffe3ull, 0xccfbddcc46206fdbull, 0x07ec4f05bd4a8fe3ull};
+    p.diag_kind = (!memcmp(internal_diag_m1, ONE, 32) && !memcmp(internal_diag_m1 + 4, ONE, 32) &&
+                   !memcmp(internal_diag_m1 + 8, TWO, 32))
+                      ? 1
+                      : 0;
+    ctx->p2_set = true;
+    return LSP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// parity probes
+// ---------------------------------------------------------------------------
+extern "C" int lsp_fr_op(lsp_ctx* ctx, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t n) {
+    if (!ctx || !a || !out || op < 0 || op > 4 || (op <= 2 && !b)) return LSP_ERR_PARAM;
+    if (n == 0) return LSP_OK;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr *da = nullptr, *db = nullptr, *dout = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&da, n * 32));
+    LSP_TRY(dev_alloc(ctx, (void**)&db, n * 32));
+    LSP_TRY(dev_alloc(ctx, (void**)&dout, n * 32));
+    LSP_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (op <= 2) LSP_CUDA(ctx, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_LAUNCH(ctx, k_fr_op, grid_for(ctx, n, 128), 128, 0, op, da, db, dout, n);
+    LSP_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, da);
+    dev_free(ctx, db);
+    dev_free(ctx, dout);
+    return LSP_OK;
+}
+
+extern "C" int lsp_poseidon2_permute(lsp_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n) {
+    if (!ctx || !in || !out) return LSP_ERR_PARAM;
+    if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
+    if (n == 0) return LSP_OK;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr *din = nullptr, *dout = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&din, n * 96));
+    LSP_TRY(dev_alloc(ctx, (void**)&dout, n * 96));
+    LSP_CUDA(ctx, cudaMemcpyAsync(din, in, n * 96, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_p2_permute<D>, grid_for(ctx, n, 128), 128, 0, ctx->p2, din, dout, n));
+    LSP_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, din);
+    dev_free(ctx, dout);
+    return LSP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// matrices
+// ---------------------------------------------------------------------------
+int lsp::mat_alloc(lsp_ctx* ctx, size_t rows, size_t width, lsp_mat** out) {
+    lsp_mat* m = new lsp_mat();
+    m->rows = rows;
+    m->width = width;
+    int rc = dev_alloc(ctx, (void**)&m->d, rows * width * 32);
+    if (rc != LSP_OK) {
+        delete m;
+        return rc;
+    }
+    *out = m;
+    return LSP_OK;
+}
+
+extern "C" int lsp_mat_upload(lsp_ctx* ctx, const uint64_t* rowmajor, size_t rows, size_t width, lsp_mat** out) {
+    if (!ctx || !rowmajor || !out || rows == 0 || width == 0) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    lsp_mat* m = nullptr;
+    LSP_TRY(mat_alloc(ctx, rows, width, &m));
+    Fr* stage = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&stage, rows * width * 32));
+    LSP_CUDA(ctx, cudaMemcpyAsync(stage, rowmajor, rows * width * 32, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_LAUNCH(ctx, k_rm_to_cm, grid_for(ctx, rows * width, 256), 256, 0, stage, m->d, rows, width, size_t(0), rows);
+    dev_free(ctx, stage);
+    *out = m;
+    return LSP_OK;
+}
+
+extern "C" int lsp_mat_download_rows(lsp_ctx* ctx, const lsp_mat* m, size_t row0, size_t nrows, uint64_t* out) {
+    if (!ctx || !m || !out || row0 + nrows > m->rows) return LSP_ERR_PARAM;
+    if (nrows == 0) return LSP_OK;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr* stage = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&stage, nrows * m->width * 32));
+    LSP_LAUNCH(ctx, k_cm_to_rm, grid_for(ctx, nrows * m->width, 256), 256, 0, m->d, stage, m->rows, m->width, row0, nrows);
+    LSP_CUDA(ctx, cudaMemcpyAsync(out, stage, nrows * m->width * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, stage);
+    return LSP_OK;
+}
+
+extern "C" int lsp_mat_download(lsp_ctx* ctx, const lsp_mat* m, uint64_t* out) {
+    if (!m) return LSP_ERR_PARAM;
+    return lsp_mat_download_rows(ctx, m, 0, m->rows, out);
+}
+
+extern "C" size_t lsp_mat_rows(const lsp_mat* m) { return m ? m->rows : 0; }
+extern "C" size_t lsp_mat_width(const lsp_mat* m) { return m ? m->width : 0; }
+
+extern "C" void lsp_mat_free(lsp_ctx* ctx, lsp_mat* m) {
+    if (!m) return;
+    if (m->owns && ctx) dev_free(ctx, m->d);
+    delete m;
+}
+
+// ---------------------------------------------------------------------------
+// Merkle MMCS
+// ---------------------------------------------------------------------------
+namespace lsp {
+
+// digests must hold 2h-1 elements; cols is a device array of `width` column pointers.
+int merkle_build(lsp_ctx* ctx, const Fr* const* d_cols, int width, size_t h, Fr* digests) {
+    if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
+    int log_h = ilog2(h);
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
+                      LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, h, 128), 128, 0, ctx->p2, d_cols, width, h, digests));
+    for (int k = 0; k < log_h; k++) {
+        size_t n_out = h >> (k + 1);
+        const Fr* in = digests + tree_layer_offset(h, k);
+        Fr* out = digests + tree_layer_offset(h, k + 1);
+        LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
+                          LSP_LAUNCH(ctx, k_compress_layer<D>, grid_for(ctx, n_out, 128), 128, 0, ctx->p2, in, out, n_out));
+    }
+    return LSP_OK;
+}
+
+// FRI commit-phase tree over a vector viewed as (len/2) rows of 2: the leaf digest of
+// row j is hash_iter([v[2j], v[2j+1]]) = one permutation = the compression function,
+// so the whole tree is compress layers applied to the vector itself.
+int merkle_build_pairs(lsp_ctx* ctx, const Fr* vec, size_t len, Fr* digests) {
+    if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
+    size_t h = len / 2;
+    int log_h = ilog2(h);
+    const Fr* in = vec;
+    for (int k = 0; k <= log_h; k++) {
+        size_t n_out = h >> k;
+        Fr* out = digests + tree_layer_offset(h, k);
+        LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
+                          LSP_LAUNCH(ctx, k_compress_layer<D>, grid_for(ctx, n_out, 128), 128, 0, ctx->p2, in, out, n_out));
+        in = out;
+    }
+    return LSP_OK;
+}
+
+}  // namespace lsp
+
+extern "C" int lsp_merkle_commit(lsp_ctx* ctx, const lsp_mat* const* mats, int n_mats, uint64_t root_out[4], lsp_tree** out) {
+    if (!ctx || !mats || n_mats <= 0 || !out) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t h = mats[0]->rows;
+    if (!is_pow2(h)) return set_err(ctx, LSP_ERR_PARAM, "matrix height %zu is not a power of two", h);
+    std::vector<const Fr*> cols;
+    for (int i = 0; i < n_mats; i++) {
+        if (!mats[i] || mats[i]->rows != h)
+            return set_err(ctx, LSP_ERR_PARAM, "mixed-height commits are not on the reference's path");
+        for (size_t c = 0; c < mats[i]->width; c++) cols.push_back(mats[i]->d + c * h);
+    }
+    lsp_tree* t = new lsp_tree();
+    t->height = h;
+    t->log_h = ilog2(h);
+    t->total_width = cols.size();
+    for (int i = 0; i < n_mats; i++) t->mats.push_back(mats[i]);
+    int rc = dev_alloc(ctx, (void**)&t->digests, (2 * h - 1) * 32);
+    if (rc == LSP_OK) rc = dev_alloc(ctx, (void**)&t->d_cols, cols.size() * sizeof(Fr*));
+    if (rc != LSP_OK) {
+        lsp_tree_free(ctx, t);
+        return rc;
+    }
+    // column-pointer table: small pageable copy, synchronous w.r.t. the host buffer
+    LSP_CUDA(ctx, cudaMemcpyAsync(t->d_cols, cols.data(), cols.size() * sizeof(Fr*), cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    rc = merkle_build(ctx, t->d_cols, int(cols.size()), h, t->digests);
+    if (rc != LSP_OK) {
+        lsp_tree_free(ctx, t);
+        return rc;
+    }
+    if (root_out) {
+        LSP_CUDA(ctx, cudaMemcpyAsync(root_out, t->digests + (2 * h - 2), 32, cudaMemcpyDeviceToHost, ctx->stream));
+        LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    *out = t;
+    return LSP_OK;
+}
+
+extern "C" int lsp_merkle_open_batch(lsp_ctx* ctx, const lsp_tree* t, size_t index, uint64_t* rows_out, uint64_t* siblings_out) {
+    if (!ctx || !t || !rows_out || !siblings_out || index >= t->height) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Fr* buf = nullptr;
+    size_t n = t->total_width + t->log_h;
+    LSP_TRY(dev_alloc(ctx, (void**)&buf, n * 32));
+    LSP_LAUNCH(ctx, k_gather_row, unsigned((t->total_width + 63) / 64), 64, 0, t->d_cols, int(t->total_width), index, buf);
+    if (t->log_h > 0)
+        LSP_LAUNCH(ctx, k_gather_siblings, 1, 64, 0, t->digests, t->height, t->log_h, index, buf + t->total_width);
+    LSP_CUDA(ctx, cudaMemcpyAsync(rows_out, buf, t->total_width * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t->log_h > 0)
+        LSP_CUDA(ctx, cudaMemcpyAsync(siblings_out, buf + t->total_width, size_t(t->log_h) * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, buf);
+    return LSP_OK;
+}
+
+extern "C" int lsp_merkle_layer(lsp_ctx* ctx, const lsp_tree* t, int layer, uint64_t* out) {
+    if (!ctx || !t || !out || layer < 0 || layer > t->log_h) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    size_t n = t->height >> layer;
+    LSP_CUDA(ctx, cudaMemcpyAsync(out, t->digests + tree_layer_offset(t->height, layer), n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSP_OK;
+}
+
+extern "C" size_t lsp_merkle_height(const lsp_tree* t) { return t ? t->height : 0; }
+
+extern "C" void lsp_tree_free(lsp_ctx* ctx, lsp_tree* t) {
+    if (!t) return;
+    if (ctx) {
+        dev_free(ctx, t->digests);
+        dev_free(ctx, (void*)t->d_cols);
+    }
+    delete t;
+}
+
+extern "C" int lsp_hash_rows(lsp_ctx* ctx, const uint64_t* rowmajor, size_t rows, size_t width, uint64_t* digests_out) {
+    if (!ctx || !rowmajor || !digests_out || rows == 0) return LSP_ERR_PARAM;
+    if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
+    if (width == 0) {  // hash_iter of an empty row is state[0] = 0 with no permutation
+        memset(digests_out, 0, rows * 32);
+        return LSP_OK;
+    }
+    lsp_mat* m = nullptr;
+    LSP_TRY(lsp_mat_upload(ctx, rowmajor, rows, width, &m));
+    std::vector<const Fr*> cols;
+    for (size_t c = 0; c < width; c++) cols.push_back(m->d + c * rows);
+    const Fr** d_cols = nullptr;
+    Fr* dig = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&d_cols, cols.size() * sizeof(Fr*)));
+    LSP_TRY(dev_alloc(ctx, (void**)&dig, rows * 32));
+    LSP_CUDA(ctx, cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(Fr*), cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, rows, 128), 128, 0, ctx->p2,
+                                                 (const Fr* const*)d_cols, int(width), rows, dig));
+    LSP_CUDA(ctx, cudaMemcpyAsync(digests_out, dig, rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    dev_free(ctx, (void*)d_cols);
+    dev_free(ctx, dig);
+    lsp_mat_free(ctx, m);
+    return LSP_OK;
+}

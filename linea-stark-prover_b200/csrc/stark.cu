@@ -1,0 +1,562 @@
+// STARK-specific kernels: device-resident Fiat-Shamir challenger, inverse
+// denominators over the LDE coset, the fused permutation-AIR quotient kernel,
+// opened values, and the FRI fold.
+//
+// Reference anchors (algorithms: published Plonky3 of the pinned era):
+//   Challenger = HashChallenger<Val,Hash,1>      bin/src/config.rs:23, bin/src/main.rs:78
+//   LineaAIR::eval -> eval_permutation           air/src/lib.rs:47-54,116-167
+//   TwoAdicFriPcs::open / FRI commit phase       bin/src/config.rs:24-25, bin/src/main.rs:58-66
+#include "stark.cuh"
+
+using namespace lsp;
+
+namespace lsp {
+
+// ===========================================================================
+// HashChallenger<Val,Hash,1> on the device.  All kernels run <<<1,1>>>: the
+// transcript is a serial chain by construction; keeping it on the device
+// removes every host round trip from prove().
+// ===========================================================================
+template <int D>
+__device__ __forceinline__ Fr ch_hash_input(const P2Params& P, const DevChallenger* ch) {
+    // PaddingFreeSponge<Perm,3,2,1>::hash_iter(input_buffer)
+    Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
+    int n = ch->n_input, i = 0;
+    for (; i + 1 < n; i += 2) {
+        s0 = ch->input[i];
+        s1 = ch->input[i + 1];
+        p2_permute<D>(P, s0, s1, s2);
+    }
+    if (i < n) {
+        s0 = ch->input[i];
+        p2_permute<D>(P, s0, s1, s2);
+    }
+    return s0;
+}
+
+// sample(): output_buffer is always empty when sample is called on this path
+// (OUT_LEN = 1 and every flush is immediately popped), so sample == flush + pop.
+template <int D>
+__device__ __forceinline__ Fr ch_sample(const P2Params& P, DevChallenger* ch) {
+    Fr out = ch_hash_input<D>(P, ch);
+    ch->input[0] = out;
+    ch->n_input = 1;
+    return out;
+}
+
+__device__ __forceinline__ void ch_observe(DevChallenger* ch, const Fr& v) {
+    if (ch->n_input < CH_CAP)
+        ch->input[ch->n_input++] = v;
+    else
+        ch->overflow = 1;
+}
+
+__global__ void k_ch_init(DevChallenger* ch) {
+    ch->n_input = 0;
+    ch->overflow = 0;
+}
+__global__ void k_ch_observe(DevChallenger* ch, const Fr* vals, int n) {
+    for (int i = 0; i < n; i++) ch_observe(ch, fr_load(vals + i));
+}
+template <int D>
+__global__ void k_ch_sample(const __grid_constant__ P2Params P, DevChallenger* ch, Fr* out) {
+    Fr v = ch_sample<D>(P, ch);
+    fr_store(out, v);
+}
+// canonical integer of a Montgomery-form element: multiply by 1
+__device__ __forceinline__ Fr fr_from_mont(const Fr& a) {
+    Fr one = fr_zero();
+    one.l[0] = 1;
+    return fr_mul(a, one);
+}
+template <int D>
+__global__ void k_ch_sample_bits(const __grid_constant__ P2Params P, DevChallenger* ch, int bits, int n, uint32_t* idx) {
+    for (int q = 0; q < n; q++) {
+        Fr c = fr_from_mont(ch_sample<D>(P, ch));
+        idx[q] = bits >= 32 ? c.l[0] : (c.l[0] & ((1u << bits) - 1u));
+    }
+}
+
+// grind: each thread tests witnesses base + tid + k*stride against a clone of the
+// challenger; the smallest passing witness of the first chunk that has one wins,
+// which makes the result deterministic (the reference's rayon find_any is not).
+template <int D>
+__global__ void __launch_bounds__(128) k_ch_grind_chunk(const __grid_constant__ P2Params P, const DevChallenger* ch, int bits,
+                                                        unsigned long long base, unsigned long long* best) {
+    unsigned long long w = base + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    // absorb everything before the final block of [input_buffer..., witness]
+    Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
+    int n = ch->n_input, i = 0;
+    for (; i + 1 < n; i += 2) {
+        s0 = ch->input[i];
+        s1 = ch->input[i + 1];
+        p2_permute<D>(P, s0, s1, s2);
+    }
+    // witness as a field element: canonical w -> Montgomery
+    Fr wf = fr_zero();
+    wf.l[0] = uint32_t(w);
+    wf.l[1] = uint32_t(w >> 32);
+    wf = fr_mul(wf, fr_const(FR_R2));
+    if (i < n) {  // odd count: last block is [input[n-1], witness]
+        s0 = ch->input[i];
+        s1 = wf;
+    } else {      // even count: last block is [witness] alone, state[1] stale
+        s0 = wf;
+    }
+    p2_permute<D>(P, s0, s1, s2);
+    Fr c = fr_from_mont(s0);
+    uint32_t low = bits >= 32 ? c.l[0] : (c.l[0] & ((1u << bits) - 1u));
+    if (low == 0) atomicMin(best, w);
+}
+template <int D>
+__global__ void k_ch_apply_witness(const __grid_constant__ P2Params P, DevChallenger* ch, const unsigned long long* best,
+                                   Fr* witness_out) {
+    unsigned long long w = *best;
+    Fr wf = fr_zero();
+    wf.l[0] = uint32_t(w);
+    wf.l[1] = uint32_t(w >> 32);
+    wf = fr_mul(wf, fr_const(FR_R2));
+    fr_store(witness_out, wf);
+    ch_observe(ch, wf);        // check_witness: observe(witness) ...
+    (void)ch_sample<D>(P, ch);  // ... then sample_bits(bits) consumes one sample
+}
+
+int challenger_init(lsp_ctx* ctx, DevChallenger* ch) {
+    LSP_LAUNCH(ctx, k_ch_init, 1, 1, 0, ch);
+    return LSP_OK;
+}
+int challenger_observe_dev(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals, int n) {
+    LSP_LAUNCH(ctx, k_ch_observe, 1, 1, 0, ch, vals, n);
+    return LSP_OK;
+}
+int challenger_sample(lsp_ctx* ctx, DevChallenger* ch, Fr* out_dev) {
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample<D>, 1, 1, 0, ctx->p2, ch, out_dev));
+    return LSP_OK;
+}
+int challenger_sample_bits(lsp_ctx* ctx, DevChallenger* ch, int bits, int n, uint32_t* idx_out) {
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample_bits<D>, 1, 1, 0, ctx->p2, ch, bits, n, idx_out));
+    return LSP_OK;
+}
+int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out) {
+    unsigned long long* best = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&best, 8));
+    if (bits == 0) {
+        LSP_CUDA(ctx, cudaMemsetAsync(best, 0, 8, ctx->stream));  // witness 0 always passes
+    } else {
+        // expected 2^bits trials; test chunks until one contains a witness (host reads one u64 per chunk)
+        const unsigned long long chunk = 1ull << 22;
+        unsigned long long h_best = ~0ull;
+        for (unsigned long long base = 0;; base += chunk) {
+            LSP_CUDA(ctx, cudaMemsetAsync(best, 0xff, 8, ctx->stream));
+            LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_grind_chunk<D>, unsigned(chunk / 128), 128, 0, ctx->p2,
+                                                         (const DevChallenger*)ch, bits, base, best));
+            LSP_CUDA(ctx, cudaMemcpyAsync(&h_best, best, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (h_best != ~0ull) break;
+            if (base > (1ull << 44)) return set_err(ctx, LSP_ERR_STATE, "grind: no witness found for %d bits", bits);
+        }
+    }
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_apply_witness<D>, 1, 1, 0, ctx->p2, ch, (const unsigned long long*)best, witness_out));
+    dev_free(ctx, best);
+    return LSP_OK;
+}
+
+// ===========================================================================
+// AIR config upload
+// ===========================================================================
+int upload_perm_cfgs(lsp_ctx* ctx, const lsp_perm_air_cfg* cfgs, int n_cfgs, size_t width, PermCfgDev* out, void** blob) {
+    if (!cfgs || n_cfgs <= 0) return set_err(ctx, LSP_ERR_PARAM, "no AIR configs");
+    std::vector<uint32_t> h;
+    // layout: [n_cols x n][ids_off x n][b_inv x n][check x n][ids...]
+    size_t total_ids = 0;
+    for (int i = 0; i < n_cfgs; i++) {
+        const lsp_perm_air_cfg& c = cfgs[i];
+        if (c.n_cols == 0 || !c.a_ids || !c.b_ids) return set_err(ctx, LSP_ERR_PARAM, "AIR config %d has no columns", i);
+        for (uint32_t k = 0; k < c.n_cols; k++)
+            if (c.a_ids[k] >= width || c.b_ids[k] >= width) return set_err(ctx, LSP_ERR_PARAM, "AIR config %d: column id out of range", i);
+        if (c.b_inverse_id >= width || c.check_id >= width) return set_err(ctx, LSP_ERR_PARAM, "AIR config %d: column id out of range", i);
+        total_ids += 2 * size_t(c.n_cols);
+    }
+    h.resize(4 * size_t(n_cfgs) + total_ids);
+    size_t off = 0;
+    for (int i = 0; i < n_cfgs; i++) {
+        h[i] = cfgs[i].n_cols;
+        h[n_cfgs + i] = uint32_t(off);
+        h[2 * n_cfgs + i] = cfgs[i].b_inverse_id;
+        h[3 * n_cfgs + i] = cfgs[i].check_id;
+        for (uint32_t k = 0; k < cfgs[i].n_cols; k++) h[4 * n_cfgs + off + k] = cfgs[i].a_ids[k];
+        for (uint32_t k = 0; k < cfgs[i].n_cols; k++) h[4 * n_cfgs + off + cfgs[i].n_cols + k] = cfgs[i].b_ids[k];
+        off += 2 * size_t(cfgs[i].n_cols);
+    }
+    uint32_t* d = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&d, h.size() * 4));
+    LSP_CUDA(ctx, cudaMemcpyAsync(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    out->n_cfgs = n_cfgs;
+    out->n_cols = d;
+    out->ids_off = d + n_cfgs;
+    out->b_inverse_id = d + 2 * n_cfgs;
+    out->check_id = d + 3 * n_cfgs;
+    out->ids = d + 4 * n_cfgs;
+    *blob = d;
+    return LSP_OK;
+}
+
+// ===========================================================================
+// Inverse denominators  E[p] = 1 / (g * w^{bitrev(p)} - z),  w = omega_{2^m}.
+//
+// 1/(x-z) over the whole coset costs ~2.6 multiplications per point and ONE
+// field inversion, by descending the squaring tree of the coset: with
+// u = z/g, u_l = u^(2^(m-l)), v a 2^(l+1)-th root of unity,
+//     1/(v - u_{l+1}) = (v + u_{l+1}) / (v^2 - u_l),   1/(-v - u_{l+1}) = (u_{l+1} - v) / (v^2 - u_l)
+// so level l+1 is one multiplication per node away from level l, and the root is
+// the scalar 1/(1 - u^(2^m)).  In bit-reversed order the children of node j
+// are 2j and 2j+1, which is exactly the storage order of the committed LDE.
+// ===========================================================================
+constexpr int INVDEN_MAX_LEVELS = 40;
+struct InvDenScalars {
+    Fr u[INVDEN_MAX_LEVELS];  // u[l] = (z/g)^(2^(m-l)), l = 0..m
+    Fr e0;                    // g^-1 / (1 - u[0])   (the g^-1 makes E the inverse of g*w - z directly)
+};
+
+__global__ void k_invden_setup(const Fr* __restrict__ z, int m, InvDenScalars* __restrict__ out) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= gridDim.x * blockDim.x) return;
+    Fr ginv = fr_const(FR_GEN_INV);
+    Fr u = fr_mul(fr_load(z + p), ginv);
+    InvDenScalars* o = out + p;
+    o->u[m] = u;
+    for (int l = m - 1; l >= 0; l--) {
+        u = fr_sqr(u);
+        o->u[l] = u;
+    }
+    Fr d = fr_sub(fr_one(), u);
+    o->e0 = fr_mul(ginv, fr_inv(d));
+}
+
+// node (level l, index j) -> factor taking E_l[j>>1... ] to E_{l}[j]: uses v = w_{2^l}^{bitrev_{l-1}(j>>1)}
+__device__ __forceinline__ Fr invden_step(const Fr& e_parent, const InvDenScalars* S, const Fr* __restrict__ tw, int m, int l_child,
+                                          size_t j_child) {
+    // parent level l = l_child-1, parent index jp = j_child>>1
+    int l = l_child - 1;
+    size_t jp = j_child >> 1;
+    Fr v = fr_load_nc(tw + (size_t(bitrev32(uint32_t(jp), l)) << (m - l - 1)));
+    Fr u = S->u[l_child];
+    Fr f = (j_child & 1) ? fr_sub(u, v) : fr_add(v, u);
+    return fr_mul(e_parent, f);
+}
+
+// One thread per node of level `la`; walks down from the root.
+__global__ void __launch_bounds__(128) k_invden_top(const InvDenScalars* __restrict__ S, const Fr* __restrict__ tw, int m, int la,
+                                                    Fr* __restrict__ out) {
+    size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (j >= (size_t(1) << la)) return;
+    Fr e = S->e0;
+    for (int l = 1; l <= la; l++) e = invden_step(e, S, tw, m, l, j >> (la - l));
+    fr_store(out + j, e);
+}
+
+// From level `la` values down to the leaves (level m): each thread owns one node of
+// level lb = m - 3 and writes its 8 leaves.
+__global__ void __launch_bounds__(128) k_invden_expand(const InvDenScalars* __restrict__ S, const Fr* __restrict__ tw, int m, int la,
+                                                       int lb, const Fr* __restrict__ top, Fr* __restrict__ out) {
+    size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
+    if (j >= (size_t(1) << lb)) return;
+    Fr e[8];
+    e[0] = fr_load_nc(top + (j >> (lb - la)));
+    for (int l = la + 1; l <= lb; l++) e[0] = invden_step(e[0], S, tw, m, l, j >> (lb - l));
+    const int depth = m - lb;  // <= 3
+    for (int d = 0; d < depth; d++) {
+        for (int i = (1 << d) - 1; i >= 0; i--) {
+            size_t jc = ((j << d) + i) << 1;
+            Fr par = e[i];
+            e[2 * i + 1] = invden_step(par, S, tw, m, lb + d + 1, jc + 1);
+            e[2 * i] = invden_step(par, S, tw, m, lb + d + 1, jc);
+        }
+    }
+    for (int i = 0; i < (1 << depth); i++) fr_store(out + (j << depth) + i, e[i]);
+}
+
+int inverse_denominators(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m, Fr* const* out) {
+    if (log_m < 1 || log_m >= INVDEN_MAX_LEVELS) return set_err(ctx, LSP_ERR_PARAM, "inverse_denominators: 2^%d unsupported", log_m);
+    const Fr* tw = nullptr;
+    LSP_TRY(twiddles(ctx, log_m, false, &tw));
+    InvDenScalars* S = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&S, sizeof(InvDenScalars) * n_points));
+    LSP_LAUNCH(ctx, k_invden_setup, 1, n_points, 0, z_dev, log_m, S);
+    int la = log_m < 10 ? log_m : 10;
+    int lb = log_m - 3 > la ? log_m - 3 : la;
+    Fr* top = nullptr;
+    if (la < log_m) LSP_TRY(dev_alloc(ctx, (void**)&top, (size_t(1) << la) * 32));
+    for (int p = 0; p < n_points; p++) {
+        Fr* dst = la < log_m ? top : out[p];
+        LSP_LAUNCH(ctx, k_invden_top, unsigned(((size_t(1) << la) + 127) / 128), 128, 0, S + p, tw, log_m, la, dst);
+        if (la < log_m)
+            LSP_LAUNCH(ctx, k_invden_expand, unsigned(((size_t(1) << lb) + 127) / 128), 128, 0, S + p, tw, log_m, la, lb,
+                       (const Fr*)top, out[p]);
+    }
+    dev_free(ctx, top);
+    dev_free(ctx, S);
+    return LSP_OK;
+}
+
+// ===========================================================================
+// Fused quotient kernel for the permutation AIR.
+// One thread per storage row p of the first N*q rows of the committed trace LDE
+// (= evaluations over g*H_{Nq} in bit-reversed order).  Natural index
+// i = bitrev(p); `next` is natural index i+q, i.e. storage row bitrev(i+q).
+// ===========================================================================
+struct QuotientArgs {
+    const Fr* lde;        // column-major, column stride = lde_rows
+    size_t lde_rows;
+    int log_n, log_q;
+    PermCfgDev cfg;
+    const Fr* publics;    // [alpha_air, delta]
+    const Fr* alpha;      // STARK folding challenge
+    const Fr* inv_first;  // 1/(x - 1)          per storage row
+    const Fr* inv_last;   // 1/(x - w_N^-1)     per storage row
+    const Fr* zh;         // per chunk c: Z_H = g^N * w_q^c - 1, then 1/Z_H   (2q entries)
+    const Fr* tw_nq;      // omega_{Nq}^j, j < Nq/2
+    const Fr* w_n_inv;    // omega_N^-1
+    Fr* chunks;           // q columns of N
+};
+
+__global__ void k_quotient_setup(int log_n, int log_q, Fr* __restrict__ zh, Fr* __restrict__ w_n_inv, Fr* __restrict__ pts) {
+    int c = threadIdx.x;
+    int q = 1 << log_q;
+    if (c < q) {
+        Fr g = fr_const(FR_GEN);
+        Fr gn = g;
+        for (int i = 0; i < log_n; i++) gn = fr_sqr(gn);
+        Fr wq = fr_pow_u32(fr_two_adic_generator(log_q), uint32_t(c));
+        Fr z = fr_sub(fr_mul(gn, wq), fr_one());
+        fr_store(zh + c, z);
+        fr_store(zh + q + c, fr_inv(z));
+    }
+    if (c == 0) {
+        Fr w = fr_two_adic_generator(log_n);
+        Fr wi = fr_pow_u32(w, uint32_t((size_t(1) << log_n) - 1));  // w^(N-1) = w^-1
+        fr_store(w_n_inv, wi);
+        fr_store(pts, fr_one());      // selector points: 1 and w_N^-1
+        fr_store(pts + 1, wi);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_constant__ QuotientArgs A) {
+    const int lnq = A.log_n + A.log_q;
+    const size_t nq = size_t(1) << lnq;
+    const uint32_t q = 1u << A.log_q;
+    const Fr alpha_air = fr_load(A.publics), delta = fr_load(A.publics + 1), alpha = fr_load(A.alpha);
+    const Fr w_n_inv = fr_load(A.w_n_inv);
+    const Fr one = fr_one();
+    for (size_t p = blockIdx.x * size_t(blockDim.x) + threadIdx.x; p < nq; p += size_t(gridDim.x) * blockDim.x) {
+        const uint32_t i = bitrev32(uint32_t(p), lnq);
+        const uint32_t i_next = (i + q) & uint32_t(nq - 1);
+        const size_t pn = bitrev32(i_next, lnq);
+        const uint32_t c = i & (q - 1);
+        // x = g * w_{Nq}^i
+        Fr wi = (i < nq / 2) ? fr_load_nc(A.tw_nq + i) : fr_neg(fr_load_nc(A.tw_nq + (i - nq / 2)));
+        if (nq == 1) wi = one;
+        Fr x = fr_mul(fr_const(FR_GEN), wi);
+        Fr zh = fr_load_nc(A.zh + c), zh_inv = fr_load_nc(A.zh + q + c);
+        Fr is_first = fr_mul(zh, fr_load_nc(A.inv_first + p));
+        Fr is_last = fr_mul(zh, fr_load_nc(A.inv_last + p));
+        Fr is_trans = fr_sub(x, w_n_inv);
+        Fr acc = fr_zero();
+        bool first_c = true;
+        for (int k = 0; k < A.cfg.n_cfgs; k++) {
+            const uint32_t nc = A.cfg.n_cols[k];
+            const uint32_t* a_ids = A.cfg.ids + A.cfg.ids_off[k];
+            const uint32_t* b_ids = a_ids + nc;
+            const Fr* col_inv = A.lde + size_t(A.cfg.b_inverse_id[k]) * A.lde_rows;
+            const Fr* col_chk = A.lde + size_t(A.cfg.check_id[k]) * A.lde_rows;
+            // Horner combinations (air/src/lib.rs:129-137,150-153): comb = comb*alpha + col
+            Fr a_l = fr_load_nc(A.lde + size_t(a_ids[0]) * A.lde_rows + p);
+            Fr b_l = fr_load_nc(A.lde + size_t(b_ids[0]) * A.lde_rows + p);
+            Fr a_n = fr_load_nc(A.lde + size_t(a_ids[0]) * A.lde_rows + pn);
+            for (uint32_t j = 1; j < nc; j++) {
+                a_l = fr_add(fr_mul(a_l, alpha_air), fr_load_nc(A.lde + size_t(a_ids[j]) * A.lde_rows + p));
+                b_l = fr_add(fr_mul(b_l, alpha_air), fr_load_nc(A.lde + size_t(b_ids[j]) * A.lde_rows + p));
+                a_n = fr_add(fr_mul(a_n, alpha_air), fr_load_nc(A.lde + size_t(a_ids[j]) * A.lde_rows + pn));
+            }
+            a_l = fr_add(a_l, delta);
+            b_l = fr_add(b_l, delta);
+            a_n = fr_add(a_n, delta);
+            Fr inv_l = fr_load_nc(col_inv + p), inv_n = fr_load_nc(col_inv + pn);
+            Fr chk_l = fr_load_nc(col_chk + p), chk_n = fr_load_nc(col_chk + pn);
+            // C0: b_ch * inv - 1                                  (:143)
+            Fr c0 = fr_sub(fr_mul(b_l, inv_l), one);
+            // C1: is_first * (check - a_ch * inv)                  (:146-148)
+            Fr c1 = fr_mul(is_first, fr_sub(chk_l, fr_mul(a_l, inv_l)));
+            // C2: is_transition * (check' - check * a_ch' * inv')  (:158-161)
+            Fr c2 = fr_mul(is_trans, fr_sub(chk_n, fr_mul(fr_mul(chk_l, a_n), inv_n)));
+            // C3: is_last * (check - 1)                            (:164-166)
+            Fr c3 = fr_mul(is_last, fr_sub(chk_l, one));
+            acc = first_c ? c0 : fr_add(fr_mul(acc, alpha), c0);
+            first_c = false;
+            acc = fr_add(fr_mul(acc, alpha), c1);
+            acc = fr_add(fr_mul(acc, alpha), c2);
+            acc = fr_add(fr_mul(acc, alpha), c3);
+        }
+        Fr qv = fr_mul(acc, zh_inv);
+        // split_evals: chunk c holds natural rows c, c+q, ...
+        fr_store(A.chunks + (size_t(c) << A.log_n) + (i >> A.log_q), qv);
+    }
+}
+
+int quotient_permutation(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, int log_n, int log_q, const PermCfgDev& cfg,
+                         const Fr* publics_dev, const Fr* alpha_dev, Fr* chunks) {
+    int lnq = log_n + log_q;
+    size_t nq = size_t(1) << lnq;
+    if (nq > lde_rows) return set_err(ctx, LSP_ERR_PARAM, "quotient domain (2^%d) exceeds the LDE (%zu rows)", lnq, lde_rows);
+    if (lnq < 1) return set_err(ctx, LSP_ERR_PARAM, "trace of height 1 with a single quotient chunk is unsupported");
+    Fr* scal = nullptr;  // zh[2q], w_n_inv, pts[2]
+    size_t q = size_t(1) << log_q;
+    LSP_TRY(dev_alloc(ctx, (void**)&scal, (2 * q + 3) * 32));
+    Fr *zh = scal, *w_n_inv = scal + 2 * q, *pts = scal + 2 * q + 1;
+    LSP_LAUNCH(ctx, k_quotient_setup, 1, unsigned(q < 32 ? 32 : q), 0, log_n, log_q, zh, w_n_inv, pts);
+    Fr* inv[2] = {nullptr, nullptr};
+    LSP_TRY(dev_alloc(ctx, (void**)&inv[0], nq * 32));
+    LSP_TRY(dev_alloc(ctx, (void**)&inv[1], nq * 32));
+    LSP_TRY(inverse_denominators(ctx, pts, 2, lnq, inv));
+    const Fr* tw = nullptr;
+    LSP_TRY(twiddles(ctx, lnq, false, &tw));
+    QuotientArgs A;
+    A.lde = lde;
+    A.lde_rows = lde_rows;
+    A.log_n = log_n;
+    A.log_q = log_q;
+    A.cfg = cfg;
+    A.publics = publics_dev;
+    A.alpha = alpha_dev;
+    A.inv_first = inv[0];
+    A.inv_last = inv[1];
+    A.zh = zh;
+    A.tw_nq = tw;
+    A.w_n_inv = w_n_inv;
+    A.chunks = chunks;
+    LSP_LAUNCH(ctx, k_quotient_permutation, grid_for(ctx, nq, 128), 128, 0, A);
+    dev_free(ctx, inv[0]);
+    dev_free(ctx, inv[1]);
+    dev_free(ctx, scal);
+    return LSP_OK;
+}
+
+// ===========================================================================
+// Opened values from coefficient form:  y[c] = sum_k coeffs[c][k] z^k.
+// (Same field element as the reference's barycentric `interpolate_coset`.)
+// ===========================================================================
+constexpr int EVAL_LO_BITS = 10;
+__global__ void __launch_bounds__(128) k_point_pow_tables(const Fr* __restrict__ z, int log_n, int lo_bits, Fr* __restrict__ lo,
+                                                          Fr* __restrict__ hi) {
+    size_t n_lo = size_t(1) << lo_bits, n_hi = size_t(1) << (log_n - lo_bits);
+    Fr base = fr_load(z);
+    for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < n_lo + n_hi; j += size_t(gridDim.x) * blockDim.x) {
+        if (j < n_lo)
+            fr_store(lo + j, fr_pow_u32(base, uint32_t(j)));
+        else
+            fr_store(hi + (j - n_lo), fr_pow_u32(base, uint32_t((j - n_lo) << lo_bits)));
+    }
+}
+
+constexpr int EVAL_COLS = 4;      // columns per thread (register budget)
+constexpr int EVAL_THREADS = 128;
+// grid: (blocks over k, column groups).  partial[(group*gridDim.x + block)*EVAL_COLS + c]
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_partial(const Fr* __restrict__ coeffs, size_t n, int width, int lo_bits,
+                                                               const Fr* __restrict__ lo, const Fr* __restrict__ hi,
+                                                               Fr* __restrict__ partial) {
+    __shared__ uint4 red[EVAL_THREADS * 2];
+    const int c0 = blockIdx.y * EVAL_COLS;
+    Fr acc[EVAL_COLS];
+#pragma unroll
+    for (int c = 0; c < EVAL_COLS; c++) acc[c] = fr_zero();
+    const size_t lo_mask = (size_t(1) << lo_bits) - 1;
+    for (size_t k = blockIdx.x * size_t(blockDim.x) + threadIdx.x; k < n; k += size_t(gridDim.x) * blockDim.x) {
+        Fr zp = fr_mul(fr_load_nc(lo + (k & lo_mask)), fr_load_nc(hi + (k >> lo_bits)));
+#pragma unroll
+        for (int c = 0; c < EVAL_COLS; c++)
+            if (c0 + c < width) acc[c] = fr_add(acc[c], fr_mul(fr_load_nc(coeffs + size_t(c0 + c) * n + k), zp));
+    }
+    // block tree reduction, one column at a time
+    for (int c = 0; c < EVAL_COLS; c++) {
+        red[threadIdx.x] = make_uint4(acc[c].l[0], acc[c].l[1], acc[c].l[2], acc[c].l[3]);
+        red[EVAL_THREADS + threadIdx.x] = make_uint4(acc[c].l[4], acc[c].l[5], acc[c].l[6], acc[c].l[7]);
+        __syncthreads();
+        for (int s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+            if (threadIdx.x < s) {
+                uint4 a0 = red[threadIdx.x], a1 = red[EVAL_THREADS + threadIdx.x];
+                uint4 b0 = red[threadIdx.x + s], b1 = red[EVAL_THREADS + threadIdx.x + s];
+                Fr a, b;
+                a.l[0] = a0.x; a.l[1] = a0.y; a.l[2] = a0.z; a.l[3] = a0.w; a.l[4] = a1.x; a.l[5] = a1.y; a.l[6] = a1.z; a.l[7] = a1.w;
+                b.l[0] = b0.x; b.l[1] = b0.y; b.l[2] = b0.z; b.l[3] = b0.w; b.l[4] = b1.x; b.l[5] = b1.y; b.l[6] = b1.z; b.l[7] = b1.w;
+                a = fr_add(a, b);
+                red[threadIdx.x] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
+                red[EVAL_THREADS + threadIdx.x] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            uint4 a0 = red[0], a1 = red[EVAL_THREADS];
+            Fr a;
+            a.l[0] = a0.x; a.l[1] = a0.y; a.l[2] = a0.z; a.l[3] = a0.w; a.l[4] = a1.x; a.l[5] = a1.y; a.l[6] = a1.z; a.l[7] = a1.w;
+            fr_store(partial + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * EVAL_COLS + c, a);
+        }
+        __syncthreads();
+    }
+}
+__global__ void k_eval_finish(const Fr* __restrict__ partial, int n_blocks, int width, Fr* __restrict__ y) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= width) return;
+    int grp = c / EVAL_COLS, cc = c % EVAL_COLS;
+    Fr acc = fr_zero();
+    for (int b = 0; b < n_blocks; b++) acc = fr_add(acc, fr_load(partial + (size_t(grp) * n_blocks + b) * EVAL_COLS + cc));
+    fr_store(y + c, acc);
+}
+
+int eval_columns_at(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, const Fr* z_dev, Fr* y_dev) {
+    int log_n = ilog2(n);
+    int lo_bits = log_n < EVAL_LO_BITS ? log_n : EVAL_LO_BITS;
+    size_t n_lo = size_t(1) << lo_bits, n_hi = size_t(1) << (log_n - lo_bits);
+    Fr* tab = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&tab, (n_lo + n_hi) * 32));
+    LSP_LAUNCH(ctx, k_point_pow_tables, unsigned((n_lo + n_hi + 127) / 128), 128, 0, z_dev, log_n, lo_bits, tab, tab + n_lo);
+    int groups = int((width + EVAL_COLS - 1) / EVAL_COLS);
+    int blocks = int((n + EVAL_THREADS - 1) / EVAL_THREADS);
+    int cap = ctx->sm_count * 4;
+    if (blocks > cap) blocks = cap;
+    Fr* partial = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&partial, size_t(groups) * blocks * EVAL_COLS * 32));
+    LSP_LAUNCH(ctx, k_eval_partial, dim3(blocks, groups), EVAL_THREADS, 0, coeffs, n, int(width), lo_bits, (const Fr*)tab,
+               (const Fr*)(tab + n_lo), partial);
+    LSP_LAUNCH(ctx, k_eval_finish, unsigned((width + 63) / 64), 64, 0, (const Fr*)partial, blocks, int(width), y_dev);
+    dev_free(ctx, partial);
+    dev_free(ctx, tab);
+    return LSP_OK;
+}
+
+// ===========================================================================
+// FRI fold (arity 2):  out[j] = (1/2 + t_j) in[2j] + (1/2 - t_j) in[2j+1],
+//                      t_j = (beta/2) * w_len^{-bitrev(j)}
+// written as  (lo+hi)/2 + t_j (lo-hi)  -> 2 multiplications per pair.
+// ===========================================================================
+__global__ void __launch_bounds__(128) k_fri_fold(const Fr* __restrict__ in, size_t h, int log_h, const Fr* __restrict__ beta,
+                                                  const Fr* __restrict__ tw_inv /* w_len^-e, e < len/2 */, Fr* __restrict__ out) {
+    Fr half_beta = fr_halve(fr_load(beta));
+    for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < h; j += size_t(gridDim.x) * blockDim.x) {
+        Fr lo = fr_load_nc(in + 2 * j), hi = fr_load_nc(in + 2 * j + 1);
+        Fr t = fr_mul(half_beta, fr_load_nc(tw_inv + bitrev32(uint32_t(j), log_h)));
+        Fr r = fr_add(fr_halve(fr_add(lo, hi)), fr_mul(t, fr_sub(lo, hi)));
+        fr_store(out + j, r);
+    }
+}
+
+int fri_fold(lsp_ctx* ctx, const Fr* in, size_t len, const Fr* beta_dev, Fr* out) {
+    size_t h = len / 2;
+    int log_len = ilog2(len);
+    const Fr* tw = nullptr;
+    LSP_TRY(twiddles(ctx, log_len, true, &tw));
+    LSP_LAUNCH(ctx, k_fri_fold, grid_for(ctx, h, 128), 128, 0, in, h, log_len - 1, beta_dev, tw, out);
+    return LSP_OK;
+}
+
+}  // namespace lsp

@@ -1,0 +1,435 @@
+"""`p3_uni_stark::prove` / `verify` over `TwoAdicFriPcs` -- oracle restatement.
+
+Reference anchors: the call sites `bin/src/main.rs:58-66` (FriConfig,
+`TwoAdicFriPcs::new`), `:80-86` (`prove`), `:90-96` (`verify`) and the type
+wiring `bin/src/config.rs:9-25`.  The algorithms are the published Plonky3
+ones of the pinned era: p3-uni-stark `prove`,
+`quotient_values`, `verify`; p3-fri `TwoAdicFriPcs::{commit,open,verify}`,
+`prover::{prove,commit_phase,answer_query}`, `verifier::{verify,verify_query}`,
+`fold_matrix` / `fold_row`; p3-commit `TwoAdicMultiplicativeCoset`;
+p3-interpolation `interpolate_coset`.
+
+Transcript choices that the unavailable fork could have made differently are
+collected in `StarkParams` / documented in DESIGN.md ("unpinned choices").
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+from . import air as A
+from .challenger import HashChallenger
+from .dft import bit_reverse_rows, coset_lde_batch, idft
+from .field import (GENERATOR, R_MOD, batch_inverse, halve, inv, log2_ceil, log2_strict,
+                    reverse_bits_len, two_adic_generator)
+from .merkle import MerkleTree, verify_batch
+from .poseidon2 import Poseidon2Params
+
+
+@dataclass
+class FriConfig:
+    """`bin/src/main.rs:58-64`."""
+    log_blowup: int = 3
+    log_final_poly_len: int = 0
+    num_queries: int = 33
+    proof_of_work_bits: int = 0
+
+
+# --------------------------------------------------------------------------
+# TwoAdicMultiplicativeCoset
+# --------------------------------------------------------------------------
+@dataclass
+class Domain:
+    log_n: int
+    shift: int
+
+    def size(self):
+        return 1 << self.log_n
+
+    def gen(self):
+        return two_adic_generator(self.log_n)
+
+    def first_point(self):
+        return self.shift
+
+    def next_point(self, x):
+        return x * self.gen() % R_MOD
+
+    def create_disjoint_domain(self, min_size):
+        return Domain(log2_ceil(min_size), self.shift * GENERATOR % R_MOD)
+
+    def split_domains(self, num_chunks):
+        lc = log2_strict(num_chunks)
+        g = self.gen()
+        return [Domain(self.log_n - lc, self.shift * pow(g, i, R_MOD) % R_MOD) for i in range(num_chunks)]
+
+    def zp_at_point(self, z):
+        return (pow(z * inv(self.shift) % R_MOD, 1 << self.log_n, R_MOD) - 1) % R_MOD
+
+    def selectors_at_point(self, z):
+        u = z * inv(self.shift) % R_MOD
+        z_h = (pow(u, 1 << self.log_n, R_MOD) - 1) % R_MOD
+        ginv = inv(self.gen())
+        return dict(is_first_row=z_h * inv((u - 1) % R_MOD) % R_MOD,
+                    is_last_row=z_h * inv((u - ginv) % R_MOD) % R_MOD,
+                    is_transition=(u - ginv) % R_MOD,
+                    inv_zeroifier=inv(z_h))
+
+    def selectors_on_coset(self, coset: "Domain"):
+        assert self.shift == 1 and coset.shift != 1 and coset.log_n >= self.log_n
+        rate_bits = coset.log_n - self.log_n
+        s_pow_n = pow(coset.shift, 1 << self.log_n, R_MOD)
+        wq = two_adic_generator(rate_bits)
+        evals = [(s_pow_n * pow(wq, i, R_MOD) - 1) % R_MOD for i in range(1 << rate_bits)]
+        cg = coset.gen()
+        xs, x = [], coset.shift
+        for _ in range(coset.size()):
+            xs.append(x)
+            x = x * cg % R_MOD
+        ginv = inv(self.gen())
+        nq = len(evals)
+
+        def single(point):
+            invs = batch_inverse([(x - point) % R_MOD for x in xs])
+            return [evals[i % nq] * invs[i] % R_MOD for i in range(len(xs))]
+
+        ez = batch_inverse(evals)
+        return dict(is_first_row=single(1), is_last_row=single(ginv),
+                    is_transition=[(x - ginv) % R_MOD for x in xs],
+                    inv_zeroifier=[ez[i % nq] for i in range(len(xs))])
+
+
+# --------------------------------------------------------------------------
+# PCS commit / quotient (A.8)
+# --------------------------------------------------------------------------
+def pcs_commit(p: Poseidon2Params, fri: FriConfig, domains_and_mats):
+    ldes = []
+    for dom, mat in domains_and_mats:
+        assert dom.size() == len(mat)
+        shift = GENERATOR * inv(dom.shift) % R_MOD
+        ldes.append(coset_lde_batch(mat, fri.log_blowup, shift))
+    tree = MerkleTree(p, ldes)
+    return tree.root, tree
+
+
+def quotient_values(cfgs, publics, trace_domain: Domain, quotient_domain: Domain,
+                    trace_on_quotient_domain, alpha):
+    qsize = quotient_domain.size()
+    sels = trace_domain.selectors_on_coset(quotient_domain)
+    next_step = 1 << (quotient_domain.log_n - trace_domain.log_n)
+    out = []
+    for i in range(qsize):
+        local = trace_on_quotient_domain[i]
+        nxt = trace_on_quotient_domain[(i + next_step) % qsize]
+        acc = A.fold_constraints(cfgs, local, nxt, publics, sels["is_first_row"][i],
+                                 sels["is_last_row"][i], sels["is_transition"][i], alpha)
+        out.append(acc * sels["inv_zeroifier"][i] % R_MOD)
+    return out
+
+
+# --------------------------------------------------------------------------
+# interpolate_coset (A.9) -- barycentric evaluation of every column at z
+# --------------------------------------------------------------------------
+def interpolate_coset(coset_evals, shift, z):
+    h = len(coset_evals)
+    log_h = log2_strict(h)
+    g = two_adic_generator(log_h)
+    pts, x = [], shift
+    gp, gpow = [], 1
+    for _ in range(h):
+        pts.append(x)
+        gp.append(gpow)
+        x = x * g % R_MOD
+        gpow = gpow * g % R_MOD
+    dinv = batch_inverse([(z - x) % R_MOD for x in pts])
+    col_scale = [gp[i] * dinv[i] % R_MOD for i in range(h)]
+    w = len(coset_evals[0])
+    sums = [0] * w
+    for i in range(h):
+        row = coset_evals[i]
+        cs = col_scale[i]
+        for c in range(w):
+            sums[c] = (sums[c] + row[c] * cs) % R_MOD
+    zerofier = (pow(z, h, R_MOD) - pow(shift, h, R_MOD)) % R_MOD
+    denom = (h % R_MOD) * pow(shift, h - 1, R_MOD) % R_MOD
+    scale = zerofier * inv(denom) % R_MOD
+    return [s * scale % R_MOD for s in sums]
+
+
+# --------------------------------------------------------------------------
+# FRI (A.10)
+# --------------------------------------------------------------------------
+def fold_matrix(beta, pairs):
+    """pairs: rows (lo, hi) of the committed (len/2) x 2 matrix."""
+    h = len(pairs)
+    log_h = log2_strict(h)
+    g_inv = inv(two_adic_generator(log_h + 1))
+    half_beta = halve(beta)
+    one_half = halve(1)
+    powers, pw = [], half_beta
+    for _ in range(h):
+        powers.append(pw)
+        pw = pw * g_inv % R_MOD
+    powers = bit_reverse_rows(powers)
+    return [((one_half + powers[j]) * pairs[j][0] + (one_half - powers[j]) * pairs[j][1]) % R_MOD
+            for j in range(h)]
+
+
+def fold_row(index, log_height, beta, e0, e1):
+    x0 = pow(two_adic_generator(log_height + 1), reverse_bits_len(index, log_height), R_MOD)
+    x1 = (-x0) % R_MOD
+    return (e0 + (beta - x0) * (e1 - e0) % R_MOD * inv((x1 - x0) % R_MOD)) % R_MOD
+
+
+def fri_commit_phase(p, fri: FriConfig, fri_input, challenger, dbg=None):
+    folded = list(fri_input)
+    commits, trees, betas = [], [], []
+    final_len = (1 << fri.log_blowup) * (1 << fri.log_final_poly_len)
+    while len(folded) > final_len:
+        leaves = [[folded[2 * j], folded[2 * j + 1]] for j in range(len(folded) // 2)]
+        tree = MerkleTree(p, [leaves])
+        challenger.observe(tree.root)
+        beta = challenger.sample()
+        folded = fold_matrix(beta, leaves)
+        commits.append(tree.root)
+        trees.append(tree)
+        betas.append(beta)
+        if dbg is not None:
+            dbg.setdefault("fri_layers", []).append(list(folded))
+    final_poly = idft(bit_reverse_rows(folded))
+    assert all(x == 0 for x in final_poly[1 << fri.log_final_poly_len:]), \
+        "All coefficients beyond final_poly_len must be zero"
+    for x in final_poly:   # all blowup*final_len coefficients are observed (unpinned choice U5)
+        challenger.observe(x)
+    if dbg is not None:
+        dbg["betas"] = betas
+    return commits, trees, final_poly
+
+
+def fri_prove(p, fri: FriConfig, fri_input, challenger, open_input, dbg=None):
+    log_max_height = log2_strict(len(fri_input))
+    commits, trees, final_poly = fri_commit_phase(p, fri, fri_input, challenger, dbg)
+    pow_witness = challenger.grind(fri.proof_of_work_bits)
+    queries = []
+    indices = []
+    for _ in range(fri.num_queries):
+        index = challenger.sample_bits(log_max_height)
+        indices.append(index)
+        steps = []
+        for i, tree in enumerate(trees):  # answer_query
+            index_i = index >> i
+            rows, proof = tree.open_batch(index_i >> 1)
+            steps.append(dict(sibling_value=rows[0][(index_i ^ 1) & 1], opening_proof=proof))
+        queries.append(dict(input_proof=open_input(index), commit_phase_openings=steps))
+    if dbg is not None:
+        dbg["query_indices"] = indices
+    return dict(commit_phase_commits=commits, query_proofs=queries, final_poly=final_poly,
+                pow_witness=pow_witness)
+
+
+def pcs_open(p, fri: FriConfig, rounds, challenger, dbg=None):
+    """rounds: list of (tree, points_per_matrix).  Fork-era order: alpha first."""
+    alpha = challenger.sample()
+    max_h = max(t.height for t, _ in rounds)
+    log_max_h = log2_strict(max_h)
+    gen = two_adic_generator(log_max_h)
+    subgroup, x = [], GENERATOR
+    for _ in range(max_h):
+        subgroup.append(x)
+        x = x * gen % R_MOD
+    subgroup = bit_reverse_rows(subgroup)
+    inv_denoms = {}
+    for tree, pts in rounds:
+        for mat, pm in zip(tree.mats, pts):
+            assert len(mat) == max_h, "all committed matrices share one height on this path"
+            for z in pm:
+                if z not in inv_denoms:
+                    inv_denoms[z] = batch_inverse([(x - z) % R_MOD for x in subgroup])
+    reduced = [0] * max_h
+    num_reduced = 0
+    opened = []
+    for tree, pts in rounds:
+        opened_round = []
+        for mat, pm in zip(tree.mats, pts):
+            opened_mat = []
+            w = len(mat[0])
+            for z in pm:
+                low = mat[:len(mat) >> fri.log_blowup]
+                ys = interpolate_coset(bit_reverse_rows(low), GENERATOR, z)
+                apo = pow(alpha, num_reduced, R_MOD)
+                apow = [pow(alpha, i, R_MOD) for i in range(w)]
+                reduced_ys = sum(a * y for a, y in zip(apow, ys)) % R_MOD
+                idn = inv_denoms[z]
+                for r in range(max_h):
+                    rr = sum(a * v for a, v in zip(apow, mat[r])) % R_MOD
+                    reduced[r] = (reduced[r] + apo * ((rr - reduced_ys) % R_MOD) % R_MOD * idn[r]) % R_MOD
+                num_reduced += w
+                opened_mat.append(ys)
+            opened_round.append(opened_mat)
+        opened.append(opened_round)
+    if dbg is not None:
+        dbg["fri_alpha"] = alpha
+        dbg["fri_input"] = list(reduced)
+
+    def open_input(index):
+        out = []
+        for tree, _ in rounds:
+            rows, proof = tree.open_batch(index >> (log_max_h - log2_strict(tree.height)))
+            out.append(dict(opened_values=rows, opening_proof=proof))
+        return out
+
+    return opened, fri_prove(p, fri, reduced, challenger, open_input, dbg)
+
+
+# --------------------------------------------------------------------------
+# prove / verify (A.7, A.11)
+# --------------------------------------------------------------------------
+def prove(p: Poseidon2Params, fri: FriConfig, cfgs, trace, publics, dbg=None):
+    """`prove(&config, &air, &mut challenger, trace, &publics)` (`bin/src/main.rs:80-86`)."""
+    challenger = HashChallenger(p, [])
+    degree = len(trace)
+    log_degree = log2_strict(degree)
+    lqd = A.log_quotient_degree(cfgs)
+    qd = 1 << lqd
+    assert lqd <= fri.log_blowup, "quotient degree exceeds the LDE blowup"
+    trace_domain = Domain(log_degree, 1)
+    trace_commit, trace_tree = pcs_commit(p, fri, [(trace_domain, trace)])
+    challenger.observe(log_degree)
+    challenger.observe(trace_commit)
+    challenger.observe_slice(publics)
+    alpha = challenger.sample()
+    quotient_domain = trace_domain.create_disjoint_domain(1 << (log_degree + lqd))
+    lde = trace_tree.mats[0]
+    toq = bit_reverse_rows(lde[:quotient_domain.size()])
+    qv = quotient_values(cfgs, publics, trace_domain, quotient_domain, toq, alpha)
+    chunks = [[[qv[i]] for i in range(c, len(qv), qd)] for c in range(qd)]
+    qc_domains = quotient_domain.split_domains(qd)
+    quotient_commit, quotient_tree = pcs_commit(p, fri, list(zip(qc_domains, chunks)))
+    challenger.observe(quotient_commit)
+    zeta = challenger.sample()
+    zeta_next = trace_domain.next_point(zeta)
+    if dbg is not None:
+        dbg.update(alpha=alpha, zeta=zeta, trace_lde=lde, quotient_values=qv,
+                   trace_digests=trace_tree.layers, quotient_ldes=quotient_tree.mats)
+    opened, fri_proof = pcs_open(p, fri, [(trace_tree, [[zeta, zeta_next]]),
+                                          (quotient_tree, [[zeta] for _ in range(qd)])], challenger, dbg)
+    return dict(commitments=dict(trace=trace_commit, quotient_chunks=quotient_commit),
+                opened_values=dict(trace_local=opened[0][0][0], trace_next=opened[0][0][1],
+                                   quotient_chunks=[opened[1][c][0] for c in range(qd)]),
+                opening_proof=fri_proof, degree_bits=log_degree)
+
+
+class VerificationError(Exception):
+    pass
+
+
+def verify(p: Poseidon2Params, fri: FriConfig, cfgs, proof, publics):
+    """`verify(&config, &air, &mut challenger, &proof, &publics)` (`bin/src/main.rs:90-96`).
+    Raises VerificationError; returns None on acceptance."""
+    challenger = HashChallenger(p, [])
+    degree_bits = proof["degree_bits"]
+    lqd = A.log_quotient_degree(cfgs)
+    qd = 1 << lqd
+    trace_domain = Domain(degree_bits, 1)
+    quotient_domain = trace_domain.create_disjoint_domain(1 << (degree_bits + lqd))
+    qc_domains = quotient_domain.split_domains(qd)
+    ov = proof["opened_values"]
+    w = A.air_width(cfgs)
+    if not (len(ov["trace_local"]) == w and len(ov["trace_next"]) == w
+            and len(ov["quotient_chunks"]) == qd and all(len(c) == 1 for c in ov["quotient_chunks"])):
+        raise VerificationError("InvalidProofShape")
+    com = proof["commitments"]
+    challenger.observe(degree_bits)
+    challenger.observe(com["trace"])
+    challenger.observe_slice(publics)
+    alpha = challenger.sample()
+    challenger.observe(com["quotient_chunks"])
+    zeta = challenger.sample()
+    zeta_next = trace_domain.next_point(zeta)
+    rounds = [
+        (com["trace"], [(trace_domain, [(zeta, ov["trace_local"]), (zeta_next, ov["trace_next"])])]),
+        (com["quotient_chunks"], [(d, [(zeta, v)]) for d, v in zip(qc_domains, ov["quotient_chunks"])]),
+    ]
+    pcs_verify(p, fri, rounds, proof["opening_proof"], challenger)
+    zps = []
+    for i, d in enumerate(qc_domains):
+        acc = 1
+        for j, o in enumerate(qc_domains):
+            if j != i:
+                acc = acc * o.zp_at_point(zeta) % R_MOD * inv(o.zp_at_point(d.first_point())) % R_MOD
+        zps.append(acc)
+    quotient = sum(zps[i] * ov["quotient_chunks"][i][0] for i in range(qd)) % R_MOD
+    sels = trace_domain.selectors_at_point(zeta)
+    folded = A.fold_constraints(cfgs, ov["trace_local"], ov["trace_next"], publics,
+                                sels["is_first_row"], sels["is_last_row"], sels["is_transition"], alpha)
+    if folded * sels["inv_zeroifier"] % R_MOD != quotient:
+        raise VerificationError("OodEvaluationMismatch")
+
+
+def pcs_verify(p, fri: FriConfig, rounds, proof, challenger):
+    alpha = challenger.sample()
+    log_global_max = len(proof["commit_phase_commits"]) + fri.log_blowup + fri.log_final_poly_len
+    betas = []
+    for c in proof["commit_phase_commits"]:
+        challenger.observe(c)
+        betas.append(challenger.sample())
+    for x in proof["final_poly"]:
+        challenger.observe(x)
+    if len(proof["query_proofs"]) != fri.num_queries:
+        raise VerificationError("InvalidProofShape")
+    if not challenger.check_witness(fri.proof_of_work_bits, proof["pow_witness"]):
+        raise VerificationError("InvalidPowWitness")
+    log_final_height = fri.log_blowup + fri.log_final_poly_len
+    for qp in proof["query_proofs"]:
+        index = challenger.sample_bits(log_global_max)
+        # open_input: reduced openings per log_height (single height on this path)
+        ros = {}
+        if len(qp["input_proof"]) != len(rounds):
+            raise VerificationError("InvalidProofShape")
+        for bo, (commit, mats) in zip(qp["input_proof"], rounds):
+            heights = [d.size() << fri.log_blowup for d, _ in mats]
+            log_bmax = log2_strict(max(heights))
+            ridx = index >> (log_global_max - log_bmax)
+            if len(set(heights)) != 1 or len(bo["opened_values"]) != len(mats):
+                raise VerificationError("InvalidProofShape")
+            if not verify_batch(p, commit, heights[0], ridx, bo["opened_values"], bo["opening_proof"]):
+                raise VerificationError("InputError(MerkleRootMismatch)")
+            for mat_opening, (dom, pvs) in zip(bo["opened_values"], mats):
+                log_h = dom.log_n + fri.log_blowup
+                rri = reverse_bits_len(index >> (log_global_max - log_h), log_h)
+                x = GENERATOR * pow(two_adic_generator(log_h), rri, R_MOD) % R_MOD
+                ap, ro = ros.get(log_h, (1, 0))
+                for z, ps_at_z in pvs:
+                    if len(ps_at_z) != len(mat_opening):
+                        raise VerificationError("InvalidProofShape")
+                    for p_at_x, p_at_z in zip(mat_opening, ps_at_z):
+                        q = (p_at_x - p_at_z) % R_MOD * inv((x - z) % R_MOD) % R_MOD
+                        ro = (ro + ap * q) % R_MOD
+                        ap = ap * alpha % R_MOD
+                ros[log_h] = (ap, ro)
+        ro_list = sorted(((lh, ro) for lh, (_, ro) in ros.items()), reverse=True)
+        # verify_query
+        if len(qp["commit_phase_openings"]) != len(betas):
+            raise VerificationError("InvalidProofShape")
+        folded_eval = 0
+        dom_index = index
+        ro_i = 0
+        for log_fh, beta, comm, op in zip(range(log_global_max - 1, log_final_height - 1, -1), betas,
+                                          proof["commit_phase_commits"], qp["commit_phase_openings"]):
+            if ro_i < len(ro_list) and ro_list[ro_i][0] == log_fh + 1:
+                folded_eval = (folded_eval + ro_list[ro_i][1]) % R_MOD
+                ro_i += 1
+            evals = [folded_eval, folded_eval]
+            evals[(dom_index ^ 1) & 1] = op["sibling_value"]
+            if not verify_batch(p, comm, 1 << log_fh, dom_index >> 1, [evals], op["opening_proof"]):
+                raise VerificationError("CommitPhaseMmcsError")
+            dom_index >>= 1
+            folded_eval = fold_row(dom_index, log_fh, beta, evals[0], evals[1])
+        if ro_i != len(ro_list):
+            raise VerificationError("InvalidProofShape")
+        x = pow(two_adic_generator(log_global_max), reverse_bits_len(dom_index, log_global_max), R_MOD)
+        ev, xp = 0, 1
+        for c in proof["final_poly"]:
+            ev = (ev + c * xp) % R_MOD
+            xp = xp * x % R_MOD
+        if ev != folded_eval:
+            raise VerificationError("FinalPolyMismatch")
