@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- prove seconds for the 3x3-column 2^19-row permutation AIR (BASELINE.json
+configs[1]) on B200, through the C ABI of liblsp_b200.so.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA prover
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU arm (C oracle port)
+
+One "step" = one full uni-STARK prove (commit trace, quotient, commit quotient, open, FRI)
+of a synthetic trace.  `value` times the prove with the trace already resident in HBM;
+`e2e` times the reference-facing call `lsp_prove_permutation` with the trace in pinned host
+memory (H2D of the trace and D2H of the proof inside the timed region).  Prints ONE JSON line.
+
+At N > 1 every rank proves its own trace (independent proofs, no data-path collective):
+weak scaling over proofs; `value` is then seconds per proof of the whole job.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+R_LIMBS = np.array([0x0a11800000000001, 0x59aa76fed0000001, 0x60b44d1e5c37b001, 0x12ab655e9a2ca556], dtype=np.uint64)
+MAC32_PER_MODMUL = 136          # CIOS on 8 x 32-bit limbs: 2*8^2 + 8
+SBOX_MULS = {3: 2, 5: 3, 7: 4, 11: 5, 17: 5}
+
+
+def random_fr_limbs(rng: np.random.Generator, n: int) -> np.ndarray:
+    """n uniform field elements as uint64[n,4] limbs (< r).  A uniform Montgomery
+    representative is a uniform element, so no conversion is needed."""
+    out = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+    out[:, 3] &= np.uint64((1 << 61) - 1)
+    while True:
+        ge = np.zeros(n, dtype=bool)
+        decided = np.zeros(n, dtype=bool)
+        for i in (3, 2, 1, 0):
+            gt = (out[:, i] > R_LIMBS[i]) & ~decided
+            lt = (out[:, i] < R_LIMBS[i]) & ~decided
+            ge |= gt
+            decided |= gt | lt
+        ge |= ~decided
+        k = int(ge.sum())
+        if k == 0:
+            return out
+        fresh = rng.integers(0, 1 << 64, size=(k, 4), dtype=np.uint64)
+        fresh[:, 3] &= np.uint64((1 << 61) - 1)
+        out[ge] = fresh
+
+
+def synthetic_ab(seed: int, c: int, n: int) -> np.ndarray:
+    """SURVEY.md 8(d) workload: c random columns `a`, `b` = the rows of `a` shuffled as whole
+    rows.  Returns uint64[n*2c, 4], row-major (a columns then b columns)."""
+    rng = np.random.default_rng(seed)
+    a = random_fr_limbs(rng, n * c).reshape(n, c, 4)
+    perm = rng.permutation(n)
+    ab = np.concatenate([a, a[perm]], axis=1)
+    return np.ascontiguousarray(ab.reshape(n * 2 * c, 4))
+
+
+def poseidon2_constants(seed: int, rounds_f: int, rounds_p: int):
+    """Stand-in for the reference's `Perm::new_from_rng(8, 22, &mut thread_rng())`
+    (bin/src/main.rs:49): seeded uniform constants, as Montgomery limbs."""
+    rng = np.random.default_rng(seed)
+    return random_fr_limbs(rng, rounds_f * 3 + rounds_p)
+
+
+ONE_MONT = np.array([0x7d1c7ffffffffff3, 0x7257f50f6ffffff2, 0x16d81575512c0fee, 0x0d4bda322bbb9a9d], dtype=np.uint64)
+TWO_MONT = np.array([0xf0277fffffffffe5, 0x8b0573200fffffe3, 0xccfbddcc46206fdb, 0x07ec4f05bd4a8fe3], dtype=np.uint64)
+
+
+def perm_counts(log_n: int, w: int, log_blowup: int, q: int, log_final: int):
+    big = 1 << (log_n + log_blowup)
+    trace = big * ((w + 1) // 2) + big - 1
+    quot = big * ((q + 1) // 2) + big - 1
+    fri = 0
+    ln = big
+    for _ in range(log_n - log_final):
+        fri += ln - 1     # len/2 leaf hashes + len/2 - 1 compressions
+        ln //= 2
+    return trace, quot, fri
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    f = [x.strip() for x in line.split(",")]
+                    if len(f) >= 8:
+                        self.rows.append(f)
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the C port of the reference prover (oracle/c), all host threads, bounded sample
+# ---------------------------------------------------------------------------------------
+def cpu_sample_prove(log_n_full: int, c: int, fri_kw: dict, sbox_d: int, budget_s: float = 20.0):
+    from oracle import cport
+    from oracle import air as OA
+    from oracle import stark as OS
+    from oracle.poseidon2 import Poseidon2Params
+    cport.set_poseidon2(Poseidon2Params.from_seed(0xB200, sbox_d=sbox_d))
+    fri = OS.FriConfig(**fri_kw)
+    cfgs = [OA.AirPermutationConfig.standard(c)]
+    w = 2 * c + 2
+    full = sum(perm_counts(log_n_full, w, fri.log_blowup, 2, fri.log_final_poly_len))
+
+    def run(log_n):
+        pub, tr, n, _ = cport.gen_trace(0xB200 + log_n, c, log_n)
+        t = time.perf_counter()
+        words = cport.prove_limbs(fri, tr, n, w, cfgs, pub)
+        dt = time.perf_counter() - t
+        assert cport.verify_limbs(fri, log_n, w, cfgs, pub, words) == 0
+        return dt
+
+    log_n = min(11, log_n_full)
+    dt = run(log_n)
+    # grow the sample until it is worth ~budget_s of CPU work (but never beyond the real size)
+    while log_n < log_n_full and dt * 2.2 < budget_s:
+        log_n += 1
+        dt = run(log_n)
+    sample = sum(perm_counts(log_n, w, fri.log_blowup, 2, fri.log_final_poly_len))
+    scale = full / sample
+    return {"sample_log_n": log_n, "sample_seconds": dt, "scale": scale, "seconds_full": dt * scale,
+            "threads": cport.threads(), "perms_per_s": sample / dt}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    fri_kw = dict(log_blowup=args.log_blowup, log_final_poly_len=0, num_queries=33, proof_of_work_bits=0)
+    vals = []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info = cpu_sample_prove(args.log_n, args.cols, fri_kw, args.sbox_d, budget_s=args.cpu_budget)
+        if i >= args.warmup:
+            vals.append(info["seconds_full"])
+    v = float(np.mean(vals))
+    sample = (f"C port of the reference prover (oracle/c, OpenMP): full prove of a 2^{info['sample_log_n']}-row trace "
+              f"took {info['sample_seconds']:.2f} s on {info['threads']} threads; scaled by Poseidon2 permutation "
+              f"count x{info['scale']:.1f} to 2^{args.log_n} rows")
+    print(json.dumps({
+        "impl": "reference", "metric": "prove_seconds", "value": v, "unit": "s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u256 (BLS12-377 Fr, Montgomery 4x64-bit)", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": v, "unit": "s", "cores": info["threads"], "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, world):
+    w = 2 * args.cols + 2
+    return {"workload": f"permutation AIR {args.cols}x{args.cols} columns (width {w}), 2^{args.log_n} rows, "
+                        f"log_blowup {args.log_blowup}, 33 queries, Poseidon2 t=3 RF=8 RP=22 d={args.sbox_d} over BLS12-377 Fr",
+            "rows": 1 << args.log_n, "width": w, "log_blowup": args.log_blowup, "quotient_chunks": 2,
+            "sbox_d": args.sbox_d, "parallelism": "single GPU" if world == 1 else f"{world} independent proofs (one per GPU)",
+            "l2": "inputs larger than L2: the 1 GiB trace LDE and 0.25 GiB digest layers are streamed every step"}
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def run_gpu(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    pkg = g.load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = pkg.Context(local_rank)
+    consts = poseidon2_constants(0xB200, 8, 22)
+    diag = np.stack([ONE_MONT, ONE_MONT, TWO_MONT])
+    ctx.check(ctx.lib.lsp_set_poseidon2(ctx.h, 3, args.sbox_d, 8, 22, pkg.ffi.as_u64p(consts), pkg.ffi.as_u64p(diag)),
+              "lsp_set_poseidon2")
+    n, c = 1 << args.log_n, args.cols
+    w = 2 * c + 2
+    fri = pkg.FriConfig(log_blowup=args.log_blowup, log_final_poly_len=0, num_queries=33, proof_of_work_bits=0)
+    cfgs = [pkg.AirPermutationConfig(range(c), range(c, 2 * c), 2 * c, 2 * c + 1)]
+    # synthetic input -> witness on the device (lsp_permutation_trace) -> host copy for the e2e leg
+    pub = random_fr_limbs(np.random.default_rng(7 + rank), 2)
+    ab = synthetic_ab(0xB200 + rank, c, n)
+    trace_dev = ctx.permutation_trace(ab, n, c, pub)
+    del ab
+    host = torch.empty((n * w, 4), dtype=torch.int64, pin_memory=True)   # pinned: the e2e leg copies from here
+    host_np = host.numpy().view(np.uint64)
+    host_np[:] = trace_dev.download_array()
+    publics_ints = pkg.from_mont_array(pub)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def prove_dev(tm=None):
+        return pkg.prove(ctx, fri, cfgs, trace_dev, publics_ints, timings=tm)
+
+    def prove_host(tm=None):
+        return pkg.prove(ctx, fri, cfgs, (host_np, n, w), publics_ints, timings=tm)
+
+    for _ in range(args.warmup):
+        prove_dev()
+    # ---- timed region: `value` (trace resident in HBM) --------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ctx.kernel_launches()
+    ctx.kernel_timing(True)
+    stage_acc = {}
+    barrier()
+    t0 = time.perf_counter()
+    stage_ms_total = 0.0
+    for _ in range(args.steps):
+        tm = {}
+        proof = prove_dev(tm)
+        stage_ms_total += sum(tm.values())
+        for k, v in tm.items():
+            stage_acc[k] = stage_acc.get(k, 0.0) + v / args.steps
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    launches = (ctx.kernel_launches() - launches0) // args.steps
+    kernel_report = ctx.kernel_timing_report()
+    ctx.kernel_timing(False)
+    # device time of a step: CUDA events recorded by the library on ITS stream around every stage
+    dev_ms = stage_ms_total / args.steps
+    # ---- e2e: host buffers, H2D + D2H inside the timed region -----------------------
+    prove_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_dev = 0.0
+    for _ in range(args.steps):
+        tm = {}
+        proof = prove_host(tm)
+        e2e_dev += sum(tm.values())
+    barrier()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+    clocks = sampler.stop()
+    proof_bytes = int(proof.words.nbytes)
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([dev_ms, wall_ms, e2e_wall_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, e2e_wall_ms = [float(x) for x in t.tolist()]
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: Poseidon2 leaf hashing of the trace LDE -----
+    big = n << args.log_blowup
+    leaf = [r for r in kernel_report if r["phase"] == "commit_trace" and r["kernel"].startswith("k_leaf_hash")][0]
+    leaf_ms = leaf["ms"] / leaf["launches"]
+    leaf_bytes = big * w * 32 + big * 32
+    hbm_peak, which = measured_peaks()
+    achieved = leaf_bytes / (leaf_ms * 1e-3) / 1e9
+    int_peak = ctx.int_peak()
+    muls_per_perm = (8 * 3 + 22) * SBOX_MULS[args.sbox_d]
+    leaf_mac = big * ((w + 1) // 2) * muls_per_perm * MAC32_PER_MODMUL
+    int_ach = leaf_mac / (leaf_ms * 1e-3)
+    tp, qp, fp = perm_counts(args.log_n, w, args.log_blowup, 2, 0)
+    kern_total = sum(r["ms"] for r in kernel_report) / args.steps
+    top = sorted(kernel_report, key=lambda r: -r["ms"])[:8]
+
+    out = {
+        "metric": "prove_seconds", "value": wall_ms / 1e3 / world, "unit": "s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": wall_ms, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u256 (BLS12-377 Fr, Montgomery 8x32-bit limbs, integer pipe)",
+        "data": "synthetic", "config": workload_config(args, world),
+        "device_ms_per_step": dev_ms,
+        "stages_ms": {k: round(v, 3) for k, v in stage_acc.items()},
+        "poseidon2_perms_per_s": (tp + qp + fp) * world / (wall_ms * 1e-3),
+        "lde_gb_per_s": (n + big) * w * 32 / (stage_acc.get("commit_trace_lde", float("nan")) * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (trace LDE, 2^%d rows x %d)" % (args.log_n + args.log_blowup, w),
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                     "traffic": None, "peak_source": which, "ms_per_launch": leaf_ms,
+                     "share_of_step": leaf["ms"] / args.steps / kern_total,
+                     "note": "integer-pipe bound kernel: see int_roofline for the binding fraction"},
+        "int_roofline": {"bound": "int32 multiply pipe", "achieved": int_ach, "peak": int_peak, "unit": "MAC32/s",
+                         "frac": int_ach / int_peak, "mac32_per_modmul": MAC32_PER_MODMUL,
+                         "modmuls_per_perm": muls_per_perm,
+                         "peak_source": "lsp_int_peak: independent IMAD.WIDE.U32 chains measured on this device"},
+        "top_kernels": [{"phase": r["phase"], "kernel": r["kernel"], "launches": r["launches"] // args.steps,
+                         "ms": round(r["ms"] / args.steps, 3)} for r in top],
+        "e2e": {"value": e2e_wall_ms / 1e3 / world, "unit": "s", "h2d_bytes_per_step": n * w * 32,
+                "d2h_bytes_per_step": proof_bytes, "device_ms": e2e_dev / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        fri_kw = dict(log_blowup=args.log_blowup, log_final_poly_len=0, num_queries=33, proof_of_work_bits=0)
+        info = cpu_sample_prove(args.log_n, c, fri_kw, args.sbox_d, budget_s=args.cpu_budget)
+        out["cpu_baseline"] = {
+            "value": info["seconds_full"], "unit": "s", "cores": info["threads"], "kind": "port",
+            "sample": (f"C port of the reference prover (oracle/c): full prove of a 2^{info['sample_log_n']}-row trace in "
+                       f"{info['sample_seconds']:.2f} s on {info['threads']} threads ({info['perms_per_s']:.3g} Poseidon2 perms/s), "
+                       f"scaled x{info['scale']:.1f} by permutation count to 2^{args.log_n} rows")}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--log-n", type=int, default=19)
+    ap.add_argument("--cols", type=int, default=3)
+    ap.add_argument("--log-blowup", type=int, default=3)
+    ap.add_argument("--sbox-d", type=int, default=5)
+    ap.add_argument("--cpu-budget", type=float, default=15.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

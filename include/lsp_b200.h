@@ -51,6 +51,14 @@ int lsp_ctx_sync(lsp_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t lsp_kernel_launches(const lsp_ctx* ctx);
 
+/* Per-kernel CUDA-event timing (off by default).  enable!=0 clears the records and starts
+ * recording; the report is JSON [{"phase","kernel","launches","ms"},...]. */
+int lsp_kernel_timing(lsp_ctx* ctx, int enable);
+int lsp_kernel_timing_report(lsp_ctx* ctx, char* buf, size_t cap);
+/* Measured issue rate of independent IMAD.WIDE.U32 (32x32+64 MACs per second) on this
+ * device: the denominator of the integer roofline the benchmark reports. */
+int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s);
+
 /* `Perm::new_from_rng(8, 22, &mut rng)` (bin/src/main.rs:49): the host draws the
  * constants and hands them over.  `constants` holds, in draw order,
  * rounds_f/2 x 3 initial external, rounds_f/2 x 3 terminal external, then
@@ -119,6 +127,15 @@ int lsp_quotient_permutation(lsp_ctx* ctx, const lsp_mat* lde_bitrev, int log_n,
 /* ---- FRI pieces of `TwoAdicFriPcs` (bin/src/config.rs:24-25) -------------- */
 /* `fold_matrix(beta, m)`: in = vector of 2h elements viewed as h rows of 2; out h elements. */
 int lsp_fri_fold(lsp_ctx* ctx, const lsp_mat* in, const uint64_t beta[4], lsp_mat** out);
+
+/* ---- witness generation ---------------------------------------------------- */
+/* `RawPermutationTrace::get_trace` + `RawTrace::get_trace` (trace/src/permutation.rs:24-93,
+ * trace/src/lib.rs:94-106): from the a/b input columns (host row-major rows x 2*n_cols, a
+ * columns first) and publics = [alpha, delta], builds the rows x (2*n_cols+2) trace
+ * a.., b.., 1/(b_comb+delta), running product.  Fails (LSP_ERR_PARAM) when the running
+ * product does not end at 1, like the reference's assert (permutation.rs:76-79). */
+int lsp_permutation_trace(lsp_ctx* ctx, const uint64_t* ab_rowmajor, size_t rows, uint32_t n_cols,
+                          const uint64_t publics[2][4], lsp_mat** trace_out);
 
 /* ---- `prove` (bin/src/main.rs:80-86) ------------------------------------- */
 typedef struct {

@@ -75,6 +75,28 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self.lib.lsp_kernel_launches(self.h))
 
+    def kernel_timing(self, enable: bool):
+        self.check(self.lib.lsp_kernel_timing(self.h, 1 if enable else 0), "lsp_kernel_timing")
+
+    def kernel_timing_report(self):
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        self.check(self.lib.lsp_kernel_timing_report(self.h, buf, len(buf)), "lsp_kernel_timing_report")
+        return json.loads(buf.value.decode())
+
+    def int_peak(self) -> float:
+        v = C.c_double()
+        self.check(self.lib.lsp_int_peak(self.h, C.byref(v)), "lsp_int_peak")
+        return v.value
+
+    def permutation_trace(self, ab_limbs: np.ndarray, n: int, c: int, publics_limbs: np.ndarray) -> "Mat":
+        """`RawPermutationTrace::get_trace` + `RawTrace::get_trace` on the device.
+        ab_limbs: uint64[n*2c,4] row-major (a columns then b columns), Montgomery limbs."""
+        h = C.c_void_p()
+        self.check(self.lib.lsp_permutation_trace(self.h, ffi.as_u64p(ab_limbs), n, c, ffi.as_u64p(publics_limbs),
+                                                  C.byref(h)), "lsp_permutation_trace")
+        return Mat(self, h)
+
     # -- Perm::new_from_rng constants handed over (bin/src/main.rs:49) --------
     def set_poseidon2(self, sbox_d, rounds_f, rounds_p, flat_constants, diag_m1=(1, 1, 2)):
         c = to_mont_array(flat_constants)

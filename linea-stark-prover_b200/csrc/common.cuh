@@ -28,6 +28,16 @@ struct lsp_ctx {
     // pinned staging for small D2H reads
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    // optional per-kernel timing (bench.py / profiles): CUDA events around every launch
+    bool timing = false;
+    const char* phase = "";
+    struct TimingRec {
+        const char* name;
+        const char* phase;
+        cudaEvent_t e0, e1;
+    };
+    std::vector<TimingRec> timing_recs;
+    std::vector<cudaEvent_t> ev_pool;
 };
 
 // Column-major ("planar") on the device: column c is the contiguous run
@@ -75,10 +85,33 @@ inline int set_err(lsp_ctx* ctx, int code, const char* fmt, ...) {
         if (rc__ != LSP_OK) return rc__; \
     } while (0)
 
+inline cudaEvent_t timing_event(lsp_ctx* ctx) {
+    cudaEvent_t e;
+    if (!ctx->ev_pool.empty()) {
+        e = ctx->ev_pool.back();
+        ctx->ev_pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+inline void timing_begin(lsp_ctx* ctx, const char* name) {
+    if (!ctx->timing) return;
+    lsp_ctx::TimingRec r{name, ctx->phase, timing_event(ctx), timing_event(ctx)};
+    cudaEventRecord(r.e0, ctx->stream);
+    ctx->timing_recs.push_back(r);
+}
+inline void timing_end(lsp_ctx* ctx) {
+    if (!ctx->timing) return;
+    cudaEventRecord(ctx->timing_recs.back().e1, ctx->stream);
+}
+
 // Launch on the ctx stream, count it, and surface launch-time errors.
 #define LSP_LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
     do {                                                                     \
+        lsp::timing_begin(ctx, #kernel);                                     \
         kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);     \
+        lsp::timing_end(ctx);                                                \
         (ctx)->launches++;                                                   \
         LSP_CUDA(ctx, cudaGetLastError());                                   \
     } while (0)

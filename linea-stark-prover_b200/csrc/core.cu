@@ -136,6 +136,11 @@ extern "C" void lsp_ctx_destroy(lsp_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& kv : ctx->tw_fwd) cudaFree(kv.second);
     for (auto& kv : ctx->tw_inv) cudaFree(kv.second);
+    for (auto& r : ctx->timing_recs) {
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -150,6 +155,96 @@ extern "C" int lsp_ctx_sync(lsp_ctx* ctx) {
 }
 
 extern "C" uint64_t lsp_kernel_launches(const lsp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int lsp_kernel_timing(lsp_ctx* ctx, int enable) {
+    if (!ctx) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (auto& r : ctx->timing_recs) {
+        ctx->ev_pool.push_back(r.e0);
+        ctx->ev_pool.push_back(r.e1);
+    }
+    ctx->timing_recs.clear();
+    ctx->timing = enable != 0;
+    return LSP_OK;
+}
+
+// JSON: [{"phase": "...", "kernel": "...", "launches": n, "ms": total}, ...] aggregated by (phase, kernel)
+extern "C" int lsp_kernel_timing_report(lsp_ctx* ctx, char* buf, size_t cap) {
+    if (!ctx || !buf || cap < 3) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<std::pair<std::string, std::pair<int, double>>> agg;
+    for (auto& r : ctx->timing_recs) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, r.e0, r.e1);
+        std::string key = std::string(r.phase) + "|" + r.name;
+        bool found = false;
+        for (auto& a : agg)
+            if (a.first == key) {
+                a.second.first++;
+                a.second.second += ms;
+                found = true;
+                break;
+            }
+        if (!found) agg.push_back({key, {1, double(ms)}});
+    }
+    std::string out = "[";
+    for (size_t i = 0; i < agg.size(); i++) {
+        size_t bar = agg[i].first.find('|');
+        char line[512];
+        snprintf(line, sizeof line, "%s{\"phase\": \"%s\", \"kernel\": \"%s\", \"launches\": %d, \"ms\": %.6f}", i ? ", " : "",
+                 agg[i].first.substr(0, bar).c_str(), agg[i].first.substr(bar + 1).c_str(), agg[i].second.first, agg[i].second.second);
+        out += line;
+    }
+    out += "]";
+    if (out.size() + 1 > cap) return set_err(ctx, LSP_ERR_PARAM, "timing report needs %zu bytes", out.size() + 1);
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return LSP_OK;
+}
+
+// Integer-pipe peak of this device: independent IMAD.WIDE.U32 chains (the instruction the
+// Montgomery product is made of), timed with CUDA events.  Denominator of the integer roofline.
+__global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, uint32_t seed, int iters) {
+    uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 17u + seed;
+    unsigned long long acc[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++) acc[c] = a + c;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
+    }
+    unsigned long long r = 0;
+#pragma unroll
+    for (int c = 0; c < 8; c++) r ^= acc[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = uint32_t(r) ^ uint32_t(r >> 32);
+}
+
+extern "C" int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s) {
+    if (!ctx || !mac32_per_s) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 8192;
+    uint32_t* out = nullptr;
+    LSP_TRY(dev_alloc(ctx, (void**)&out, size_t(blocks) * threads * 4));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int r = 0; r < 6; r++) {
+        cudaEventRecord(e0, ctx->stream);
+        k_int_peak<<<blocks, threads, 0, ctx->stream>>>(out, uint32_t(r), iters);
+        cudaEventRecord(e1, ctx->stream);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (r >= 2 && ms < best) best = ms;
+    }
+    ctx->launches += 6;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    dev_free(ctx, out);
+    LSP_CUDA(ctx, cudaGetLastError());
+    *mac32_per_s = double(blocks) * threads * iters * 8.0 / (best * 1e-3);
+    return LSP_OK;
+}
 
 static bool limbs_reduced(const uint64_t* l) {
     static const uint64_t P[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};

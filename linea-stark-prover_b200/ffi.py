@@ -41,6 +41,10 @@ SIGNATURES = {
     "lsp_last_error": (C.c_char_p, [vp]),
     "lsp_ctx_sync": (C.c_int, [vp]),
     "lsp_kernel_launches": (C.c_uint64, [vp]),
+    "lsp_kernel_timing": (C.c_int, [vp, C.c_int]),
+    "lsp_kernel_timing_report": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
+    "lsp_int_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
+    "lsp_permutation_trace": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, u64p, C.POINTER(vp)]),
     "lsp_set_poseidon2": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, u64p, u64p]),
     "lsp_fr_op": (C.c_int, [vp, C.c_int, u64p, u64p, u64p, C.c_size_t]),
     "lsp_poseidon2_permute": (C.c_int, [vp, u64p, u64p, C.c_size_t]),

@@ -305,6 +305,7 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     mark();  // 0
 
     // ---- commit to trace data ---------------------------------------------------
+    ctx->phase = "commit_trace";
     Fr *coef_t = nullptr, *lde_t = nullptr, *dig_t = nullptr;
     LSP_TRY(S.get((void**)&coef_t, n * W * 32));
     LSP_TRY(S.get((void**)&lde_t, L * W * 32));
@@ -326,12 +327,14 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     LSP_TRY(challenger_sample(ctx, ch, sc + S_ALPHA));
 
     // ---- compute quotient polynomial -------------------------------------------
+    ctx->phase = "quotient";
     Fr* chunks = nullptr;
     LSP_TRY(S.get((void**)&chunks, size_t(q) * n * 32));
     LSP_TRY(quotient_permutation(ctx, lde_t, L, log_n, log_q, cfg_dev, sc + S_PUB0, sc + S_ALPHA, chunks));
     mark();  // 3
 
     // ---- commit to quotient poly chunks ----------------------------------------
+    ctx->phase = "commit_quotient";
     Fr *coef_q = nullptr, *lde_q = nullptr, *dig_q = nullptr;
     LSP_TRY(S.get((void**)&coef_q, size_t(q) * n * 32));
     LSP_TRY(S.get((void**)&lde_q, size_t(q) * L * 32));
@@ -353,6 +356,7 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     LSP_LAUNCH(ctx, k_open_points, 1, 32, 0, sc + S_ZETA, log_n, log_q, sc + S_ZETA_NEXT, sc + S_CHUNK_PT);
 
     // ---- open --------------------------------------------------------------------
+    ctx->phase = "open";
     // (fork-era order) the batching challenge is sampled before the openings
     LSP_TRY(challenger_sample(ctx, ch, sc + S_ALPHA_FRI));
     LSP_TRY(eval_columns_at(ctx, coef_t, n, W, sc + S_ZETA, p_local));
@@ -384,6 +388,7 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     mark();  // 5
 
     // ---- FRI commit phase ------------------------------------------------------
+    ctx->phase = "fri_commit";
     Fr* fri_digests = nullptr;
     LSP_TRY(S.get((void**)&fri_digests, 2 * L * 32));
     Fr* beta = nullptr;
@@ -411,6 +416,7 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     mark();  // 6
 
     // ---- grind + query phase ---------------------------------------------------
+    ctx->phase = "fri_query";
     LSP_TRY(challenger_grind(ctx, ch, int(fri->proof_of_work_bits), p_pow));
     uint32_t* idx = nullptr;
     LSP_TRY(S.get((void**)&idx, fri->num_queries * 4));
@@ -439,6 +445,7 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     mark();  // 7
     LSP_CUDA(ctx, cudaMemcpyAsync(proof_out, proof, proof_elems * 32, cudaMemcpyDeviceToHost, ctx->stream));
     mark();  // 8
+    ctx->phase = "";
     LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, &ch->overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     int overflow = *(volatile int*)ctx->pinned;

@@ -128,3 +128,53 @@ def test_prove_rejects_bad_shapes(pkg, gctx):
         pkg.prove(gctx, pkg.FriConfig(log_blowup=0), g, trace, publics)     # quotient degree > blowup
     with pytest.raises(pkg.BackendError):
         pkg.prove(gctx, pkg.FriConfig(), g, [r[:-1] for r in trace], publics)  # AIR width != trace width
+
+
+@pytest.mark.parametrize("log_n,c", [(0, 1), (3, 3), (7, 2), (11, 3), (13, 1)])
+def test_permutation_witness_on_device(pkg, gctx, log_n, c):
+    """lsp_permutation_trace == RawPermutationTrace::get_trace + RawTrace::get_trace."""
+    import numpy as np
+    n = 1 << log_n
+    rng = F.SplitMix64(70 + log_n)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    a, b = OT.synthetic_permutation_input(9 + log_n, c, n)
+    _, cols = OT.permutation_columns(a, b, alpha, delta)
+    exp = OT.row_major(cols)
+    ab = pkg.to_mont_array([x for i in range(n) for x in [col[i] for col in a] + [col[i] for col in b]])
+    got = gctx.permutation_trace(ab, n, c, pkg.to_mont_array([alpha, delta]))
+    assert got.rows() == exp
+    # a non-permutation trips the reference's last-row assertion
+    if n > 1:
+        bad = ab.copy()
+        bad[0] = pkg.to_mont_array([12345])[0]
+        with pytest.raises(pkg.BackendError, match="check column should be 1"):
+            gctx.permutation_trace(bad, n, c, pkg.to_mont_array([alpha, delta]))
+
+
+def test_full_size_prove_verifies_and_matches_cpu_port(pkg):
+    """BASELINE configs[1]: 3x3 columns, 2^19 rows.  The GPU proof must be accepted by the
+    (restated) verifier and be bit-identical to the multi-threaded CPU port's proof."""
+    import os
+    import numpy as np
+    from oracle import cport
+    from oracle.poseidon2 import Poseidon2Params
+    log_n = int(os.environ.get("LSP_FULL_LOG_N", "19"))
+    c = 3
+    p = Poseidon2Params.from_seed(0xB200, sbox_d=5)
+    cport.set_poseidon2(p)
+    ctx = pkg.Context(0)
+    ctx.set_poseidon2(p.sbox_d, p.rounds_f, p.rounds_p, p.flat_constants(), p.internal_diag_m1)
+    pub, tr, n, w = cport.gen_trace(0xB200, c, log_n)
+    fri = OS.FriConfig()
+    cfgs = [OA.AirPermutationConfig.standard(c)]
+    gproof = pkg.prove(ctx, pkg.FriConfig(), _gpu_cfgs(pkg, cfgs), (tr, n, w), pkg.from_mont_array(pub))
+    assert cport.verify_limbs(fri, log_n, w, cfgs, pub, gproof.words) == 0
+    bad = gproof.words.copy()
+    bad[4 * 5] ^= 1
+    assert cport.verify_limbs(fri, log_n, w, cfgs, pub, bad) != 0
+    cwords = cport.prove_limbs(fri, tr, n, w, cfgs, pub)
+    assert np.array_equal(cwords, gproof.words)
+    # the device-side witness generator reproduces the CPU port's trace from its a/b columns
+    ab = np.ascontiguousarray(tr.reshape(n, w, 4)[:, :2 * c, :].reshape(n * 2 * c, 4))
+    assert np.array_equal(ctx.permutation_trace(ab, n, c, pub).download_array(), tr)
+    ctx.close()
