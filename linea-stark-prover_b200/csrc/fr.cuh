@@ -258,12 +258,20 @@ __device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
 }
 __device__ __forceinline__ Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
 
+// Out-of-line product (arguments and result travel in registers, ~20 MOVs per call).
+// Used where many products follow each other (Poseidon2 S-boxes, exponentiations): one
+// 4 KiB body shared by every call site keeps those loops inside the instruction cache --
+// with the product inlined a Poseidon2 permutation is ~84 KiB of straight-line code and
+// the leaf-hash kernel stalls on instruction fetch (profiles/r1a: stall_no_instruction).
+static __device__ __noinline__ Fr fr_mul_call(Fr a, Fr b) { return fr_mul(a, b); }
+__device__ __forceinline__ Fr fr_sqr_call(const Fr& a) { return fr_mul_call(a, a); }
+
 // a^e for a small runtime exponent (e < 2^32)
 __device__ __forceinline__ Fr fr_pow_u32(Fr a, uint32_t e) {
     Fr r = fr_one();
     while (e) {
-        if (e & 1u) r = fr_mul(r, a);
-        a = fr_sqr(a);
+        if (e & 1u) r = fr_mul_call(r, a);
+        a = fr_sqr_call(a);
         e >>= 1;
     }
     return r;
@@ -277,8 +285,8 @@ static __device__ __noinline__ Fr fr_inv(const Fr& a) {
     // top set bit of r-2 is bit 252 = bit 28 of limb 7; start below it
     for (int i = 7; i >= 0; i--) {
         for (int b = (i == 7 ? 27 : 31); b >= 0; b--) {
-            r = fr_sqr(r);
-            if ((ex[i] >> b) & 1u) r = fr_mul(r, a);
+            r = fr_sqr_call(r);
+            if ((ex[i] >> b) & 1u) r = fr_mul_call(r, a);
         }
     }
     return r;

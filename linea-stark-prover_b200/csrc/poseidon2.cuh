@@ -32,21 +32,21 @@ struct P2Params {
 template <int D>
 __device__ __forceinline__ Fr p2_sbox(const Fr& x) {
     if (D == 3) {
-        return fr_mul(fr_sqr(x), x);
+        return fr_mul_call(fr_sqr_call(x), x);
     } else if (D == 5) {
-        Fr x2 = fr_sqr(x);
-        return fr_mul(fr_sqr(x2), x);
+        Fr x2 = fr_sqr_call(x);
+        return fr_mul_call(fr_sqr_call(x2), x);
     } else if (D == 7) {
-        Fr x2 = fr_sqr(x);
-        Fr x4 = fr_sqr(x2);
-        return fr_mul(fr_mul(x4, x2), x);
+        Fr x2 = fr_sqr_call(x);
+        Fr x4 = fr_sqr_call(x2);
+        return fr_mul_call(fr_mul_call(x4, x2), x);
     } else if (D == 11) {
-        Fr x2 = fr_sqr(x);
-        Fr x8 = fr_sqr(fr_sqr(x2));
-        return fr_mul(fr_mul(x8, x2), x);
+        Fr x2 = fr_sqr_call(x);
+        Fr x8 = fr_sqr_call(fr_sqr_call(x2));
+        return fr_mul_call(fr_mul_call(x8, x2), x);
     } else {  // 17
-        Fr x16 = fr_sqr(fr_sqr(fr_sqr(fr_sqr(x))));
-        return fr_mul(x16, x);
+        Fr x16 = fr_sqr_call(fr_sqr_call(fr_sqr_call(fr_sqr_call(x))));
+        return fr_mul_call(x16, x);
     }
 }
 
@@ -83,9 +83,9 @@ __device__ __noinline__ void p2_permute(const P2Params& P, Fr& s0, Fr& s1, Fr& s
         for (int r = 0; r < P.rounds_p; r++) {
             s0 = p2_sbox<D>(fr_add(s0, P.internal[r]));
             Fr t = fr_add(fr_add(s0, s1), s2);
-            s0 = fr_add(fr_mul(s0, P.diag_m1[0]), t);
-            s1 = fr_add(fr_mul(s1, P.diag_m1[1]), t);
-            s2 = fr_add(fr_mul(s2, P.diag_m1[2]), t);
+            s0 = fr_add(fr_mul_call(s0, P.diag_m1[0]), t);
+            s1 = fr_add(fr_mul_call(s1, P.diag_m1[1]), t);
+            s2 = fr_add(fr_mul_call(s2, P.diag_m1[2]), t);
         }
     }
 #pragma unroll 1
