@@ -163,6 +163,22 @@ int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp
                               const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
                               uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
 
+/* ---- multi-GPU: one proof sharded by row ranges of the LDE ---------- */
+typedef struct lsp_comm lsp_comm;
+/* NCCL bootstrap: rank 0 calls lsp_nccl_unique_id, ships the 128 bytes to the other ranks
+ * (torch.distributed / MPI / a file), every rank calls lsp_comm_init_nccl on its own ctx. */
+int lsp_nccl_unique_id(uint8_t out[128]);
+int lsp_comm_init_nccl(lsp_ctx* ctx, int rank, int world, const uint8_t unique_id[128], lsp_comm** out);
+/* All `world` ranks hosted by this process on ctx's device, collectives replaced by device
+ * copies: the same sharded code path on a single GPU (tests, 1-GPU boxes). */
+int lsp_comm_init_local(lsp_ctx* ctx, int world, lsp_comm** out);
+void lsp_comm_destroy(lsp_comm* comm);
+/* `prove` sharded over comm's ranks (world a power of two <= 2^log_blowup).  Every rank
+ * passes the same trace and receives the same proof, bit-identical to lsp_prove_permutation. */
+int lsp_prove_permutation_sharded(lsp_comm* comm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows,
+                                  size_t width, const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                                  uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -397,3 +397,81 @@ def fri_fold(ctx: Context, vec: Mat, beta: int) -> Mat:
     h = C.c_void_p()
     ctx.check(ctx.lib.lsp_fri_fold(ctx.h, vec.h, ffi.as_u64p(b), C.byref(h)), "lsp_fri_fold")
     return Mat(ctx, h)
+
+
+# ---------------------------------------------------------------------------
+# multi-GPU: one proof sharded over ranks
+# ---------------------------------------------------------------------------
+class Comm:
+    """`lsp_comm`: either NCCL over one process per GPU, or all ranks emulated on one device."""
+
+    def __init__(self, ctx: Context, h, world: int, rank: int):
+        self.ctx, self.h, self.world, self.rank = ctx, h, world, rank
+
+    @staticmethod
+    def local(ctx: Context, world: int) -> "Comm":
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lsp_comm_init_local(ctx.h, world, C.byref(h)), "lsp_comm_init_local")
+        return Comm(ctx, h, world, 0)
+
+    @staticmethod
+    def nccl(ctx: Context, rank: int, world: int, unique_id: bytes) -> "Comm":
+        assert len(unique_id) == 128
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.lsp_comm_init_nccl(ctx.h, rank, world, buf, C.byref(h)), "lsp_comm_init_nccl")
+        return Comm(ctx, h, world, rank)
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = ffi.load().lsp_nccl_unique_id(buf)
+        if rc != 0:
+            raise BackendError(f"lsp_nccl_unique_id failed ({rc}): libnccl.so.2 not loadable")
+        return bytes(buf)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.lsp_comm_destroy(self.h)
+            self.h = None
+
+
+def shard_plan(log_n: int, log_blowup: int, world: int, rank: int) -> dict:
+    """Which part of the committed matrices a rank owns: storage rows [row0, row0+rows) of the
+    bit-reversed LDE = `cosets` (exponents c of shift*w_L^c) of the evaluation domain."""
+    big = 1 << (log_n + log_blowup)
+    if world & (world - 1) or world > (1 << log_blowup):
+        raise BackendError(f"{world} ranks need a power of two <= 2^log_blowup = {1 << log_blowup}")
+    rows = big // world
+    blocks = (1 << log_blowup) // world
+    rev = lambda x: int(format(x, f"0{log_blowup}b")[::-1], 2) if log_blowup else 0
+    return dict(row0=rank * rows, rows=rows, blocks=list(range(rank * blocks, (rank + 1) * blocks)),
+                cosets=[rev(b) for b in range(rank * blocks, (rank + 1) * blocks)])
+
+
+def prove_sharded(comm: Comm, fri: FriConfig, cfgs, trace, publics, timings=None):
+    """`prove` with the LDE / Merkle / FRI work sharded over comm's ranks.  Same proof as `prove`."""
+    ctx = comm.ctx
+    cf = fri.c_struct()
+    arr, keep = _c_cfgs(cfgs)
+    pub = to_mont_array(publics)
+    tm = np.zeros(8, dtype=np.float32)
+    if isinstance(trace, tuple):
+        limbs, n, w = trace
+    else:
+        n, w = len(trace), len(trace[0])
+        limbs = to_mont_array([x for r in trace for x in r])
+    if n & (n - 1) or n == 0:
+        raise BackendError(f"trace height {n} is not a power of two")
+    log_n = n.bit_length() - 1
+    words = int(ctx.lib.lsp_proof_words(log_n, w, 1, C.byref(cf)))
+    if words == 0:
+        raise BackendError("unsupported FRI parameters for this trace height")
+    out = np.empty(words, dtype=np.uint64)
+    rc = ctx.lib.lsp_prove_permutation_sharded(comm.h, C.byref(cf), ffi.as_u64p(limbs), n, w, arr, len(cfgs),
+                                               ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    ctx.check(rc, "lsp_prove_permutation_sharded")
+    if timings is not None:
+        timings.update({k: float(v) for k, v in zip(STAGE_NAMES, tm)})
+    del keep
+    return Proof(out, log_n, w, 1, fri)

@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(128) k_p2_permute(const __grid_constant__ P2Pa
 // the concatenation of that row in every matrix (overwrite mode, rate 2).
 // cols[] are column base pointers (column-major storage => coalesced across rows).
 template <int D>
-__global__ void __launch_bounds__(128) k_leaf_hash(const __grid_constant__ P2Params P, const Fr* const* __restrict__ cols,
+__global__ void __launch_bounds__(128, 8) k_leaf_hash(const __grid_constant__ P2Params P, const Fr* const* __restrict__ cols,
                                                    int width, size_t rows, Fr* __restrict__ digests) {
     for (size_t r = blockIdx.x * size_t(blockDim.x) + threadIdx.x; r < rows; r += size_t(gridDim.x) * blockDim.x) {
         Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(128) k_leaf_hash(const __grid_constant__ P2Par
 
 // One Merkle layer: out[i] = compress(in[2i], in[2i+1]).
 template <int D>
-__global__ void __launch_bounds__(128) k_compress_layer(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
+__global__ void __launch_bounds__(128, 8) k_compress_layer(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
                                                         Fr* __restrict__ out, size_t n_out) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n_out; i += size_t(gridDim.x) * blockDim.x) {
         Fr l = fr_load(in + 2 * i), r = fr_load(in + 2 * i + 1);

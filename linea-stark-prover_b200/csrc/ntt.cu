@@ -36,10 +36,12 @@ __global__ void __launch_bounds__(128) k_gen_twiddles(Fr* __restrict__ tw, int l
 //   lo[c][j] = S_c^j            j < 2^lo_bits
 //   hi[c][j] = S_c^(j<<lo_bits) j < 2^(log_n - lo_bits)
 __global__ void __launch_bounds__(128) k_coset_pow_tables(Fr* __restrict__ lo, Fr* __restrict__ hi, const Fr* __restrict__ shift, int log_n,
-                                                          int added_bits, int lo_bits) {
+                                                          int added_bits, int lo_bits, int block0) {
+    // destination row block (block0 + blockIdx.y) of the bit-reversed LDE holds coset bitrev(block)
     int c = blockIdx.y;
     int log_l = log_n + added_bits;
-    Fr base = fr_mul(fr_load(shift), fr_pow_u32(fr_two_adic_generator(log_l), uint32_t(c)));
+    uint32_t coset = bitrev32(uint32_t(block0 + c), added_bits);
+    Fr base = fr_mul(fr_load(shift), fr_pow_u32(fr_two_adic_generator(log_l), coset));
     size_t n_lo = size_t(1) << lo_bits, n_hi = size_t(1) << (log_n - lo_bits);
     for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < n_lo + n_hi; j += size_t(gridDim.x) * blockDim.x) {
         if (j < n_lo)
@@ -58,7 +60,6 @@ struct NttPass {
     int log_n;          // transform size
     int bit_lo, t;      // this pass handles index bits [bit_lo, bit_lo+t)
     int bitrev_load;    // gather src at bitrev_{log_n}(index)
-    int dst_block_bitrev_bits;  // forward LDE: coset z is written to row block bitrev(z)
     const Fr* pow_lo;   // optional coset power tables (per z)
     const Fr* pow_hi;
     int pow_lo_bits;
@@ -93,8 +94,7 @@ __global__ void __launch_bounds__(512) k_ntt_pass(const __grid_constant__ NttPas
     const size_t base = (idx_hi << (P.bit_lo + t)) | idx_lo;  // + j << bit_lo
     const int z = blockIdx.z;
     const Fr* src = P.src + blockIdx.y * P.src_col_stride + z * P.src_z_stride;
-    size_t dst_z = P.dst_block_bitrev_bits ? bitrev32(uint32_t(z), P.dst_block_bitrev_bits) : size_t(z);
-    Fr* dst = P.dst + blockIdx.y * P.dst_col_stride + dst_z * P.dst_z_stride;
+    Fr* dst = P.dst + blockIdx.y * P.dst_col_stride + z * P.dst_z_stride;
 
     for (int j = threadIdx.x; j < tile; j += blockDim.x) {
         size_t g = base + (size_t(j) << P.bit_lo);
@@ -237,13 +237,17 @@ int interpolate_columns(lsp_ctx* ctx, const Fr* in, size_t n, size_t width, Fr* 
     return LSP_OK;
 }
 
-// out (L x W, column-major, bit-reversed row order) from coefficients (N x W).
-int coset_evaluate(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift, Fr* out) {
+// Row blocks [block0, block0 + n_blocks) of the bit-reversed LDE (each block = N rows = one
+// coset) from coefficients (N x W).  `out` is column-major with `out_col_stride` rows per
+// column and receives the blocks back to back.  block0 = 0, n_blocks = 2^added_bits is the
+// whole LDE; a rank of a sharded prove asks for its own range only.
+int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift, int block0,
+                          int n_blocks, Fr* out, size_t out_col_stride) {
     int log_n = ilog2(n);
-    size_t big = n << added_bits;
-    int n_cosets = 1 << added_bits;
     if (log_n == 0) {  // a constant polynomial
-        LSP_LAUNCH(ctx, k_broadcast_rows, grid_for(ctx, width * big, 256), 256, 0, coeffs, out, width, big);
+        for (size_t c = 0; c < width; c++)
+            LSP_LAUNCH(ctx, k_broadcast_rows, grid_for(ctx, size_t(n_blocks), 256), 256, 0, coeffs + c, out + c * out_col_stride, size_t(1),
+                       size_t(n_blocks));
         return LSP_OK;
     }
     const Fr* tw = nullptr;
@@ -251,11 +255,11 @@ int coset_evaluate(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int a
     int lo_bits = log_n < 10 ? log_n : 10;
     size_t n_lo = size_t(1) << lo_bits, n_hi = size_t(1) << (log_n - lo_bits);
     Fr *pow_lo = nullptr, *pow_hi = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&pow_lo, n_cosets * n_lo * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&pow_hi, n_cosets * n_hi * 32));
+    LSP_TRY(dev_alloc(ctx, (void**)&pow_lo, n_blocks * n_lo * 32));
+    LSP_TRY(dev_alloc(ctx, (void**)&pow_hi, n_blocks * n_hi * 32));
     {
-        dim3 grid((unsigned)((n_lo + n_hi + 127) / 128), (unsigned)n_cosets);
-        LSP_LAUNCH(ctx, k_coset_pow_tables, grid, 128, 0, pow_lo, pow_hi, shift, log_n, added_bits, lo_bits);
+        dim3 grid((unsigned)((n_lo + n_hi + 127) / 128), (unsigned)n_blocks);
+        LSP_LAUNCH(ctx, k_coset_pow_tables, grid, 128, 0, pow_lo, pow_hi, shift, log_n, added_bits, lo_bits, block0);
     }
     std::vector<int> ts;
     split_passes(log_n, ts);
@@ -265,38 +269,34 @@ int coset_evaluate(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int a
         NttPass P;
         memset(&P, 0, sizeof P);
         P.dst = out;
-        P.dst_col_stride = big;
+        P.dst_col_stride = out_col_stride;
         P.dst_z_stride = n;
-        P.dst_block_bitrev_bits = added_bits;
-        if (p == 0) {
+        if (p == 0) {  // coefficients (shared by every coset) -> destination block z, scaled by the coset powers
             P.src = coeffs;
             P.src_col_stride = n;
             P.src_z_stride = 0;
             P.pow_lo = pow_lo;
             P.pow_hi = pow_hi;
             P.pow_lo_bits = lo_bits;
-        } else {  // in place on the already-permuted destination blocks
+        } else {  // in place on the destination blocks
             P.src = out;
-            P.src_col_stride = big;
-            P.src_z_stride = 0;  // handled below
+            P.src_col_stride = out_col_stride;
+            P.src_z_stride = n;
         }
         P.tw = tw;
         P.log_n = log_n;
         P.bit_lo = bit;
         P.t = ts[p];
-        if (p == 0) {
-            LSP_TRY(launch_pass(ctx, true, P, width, n_cosets));
-        } else {
-            // source block = destination block: run the in-place passes with z already
-            // mapped (bitrev is an involution, so iterating z over blocks directly is fine)
-            P.dst_block_bitrev_bits = 0;
-            P.src_z_stride = n;
-            LSP_TRY(launch_pass(ctx, true, P, width, n_cosets));
-        }
+        LSP_TRY(launch_pass(ctx, true, P, width, n_blocks));
     }
     dev_free(ctx, pow_lo);
     dev_free(ctx, pow_hi);
     return LSP_OK;
+}
+
+// out (L x W, column-major, bit-reversed row order) from coefficients (N x W).
+int coset_evaluate(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift, Fr* out) {
+    return coset_evaluate_blocks(ctx, coeffs, n, width, added_bits, shift, 0, 1 << added_bits, out, n << added_bits);
 }
 
 }  // namespace lsp

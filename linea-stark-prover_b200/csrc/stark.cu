@@ -259,9 +259,11 @@ __global__ void __launch_bounds__(128) k_invden_top(const InvDenScalars* __restr
 // From level `la` values down to the leaves (level m): each thread owns one node of
 // level lb = m - 3 and writes its 8 leaves.
 __global__ void __launch_bounds__(128) k_invden_expand(const InvDenScalars* __restrict__ S, const Fr* __restrict__ tw, int m, int la,
-                                                       int lb, const Fr* __restrict__ top, Fr* __restrict__ out) {
+                                                       int lb, const Fr* __restrict__ top, Fr* __restrict__ out, size_t j0, size_t n_nodes) {
     size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x;
-    if (j >= (size_t(1) << lb)) return;
+    if (j >= n_nodes) return;
+    j += j0;
+    out -= j0 << (m - lb);  // out[0] is leaf j0 << depth
     Fr e[8];
     e[0] = fr_load_nc(top + (j >> (lb - la)));
     for (int l = la + 1; l <= lb; l++) e[0] = invden_step(e[0], S, tw, m, l, j >> (lb - l));
@@ -277,7 +279,7 @@ __global__ void __launch_bounds__(128) k_invden_expand(const InvDenScalars* __re
     for (int i = 0; i < (1 << depth); i++) fr_store(out + (j << depth) + i, e[i]);
 }
 
-int inverse_denominators(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m, Fr* const* out) {
+int inverse_denominators_range(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m, size_t p0, size_t count, Fr* const* out) {
     if (log_m < 1 || log_m >= INVDEN_MAX_LEVELS) return set_err(ctx, LSP_ERR_PARAM, "inverse_denominators: 2^%d unsupported", log_m);
     const Fr* tw = nullptr;
     LSP_TRY(twiddles(ctx, log_m, false, &tw));
@@ -286,18 +288,29 @@ int inverse_denominators(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m,
     LSP_LAUNCH(ctx, k_invden_setup, 1, n_points, 0, z_dev, log_m, S);
     int la = log_m < 10 ? log_m : 10;
     int lb = log_m - 3 > la ? log_m - 3 : la;
+    const int depth = log_m - lb;
+    const bool direct = la == log_m;
+    if (!direct && ((p0 | count) & ((size_t(1) << depth) - 1)))
+        return set_err(ctx, LSP_ERR_PARAM, "inverse_denominators: range must be aligned to %d rows", 1 << depth);
     Fr* top = nullptr;
-    if (la < log_m) LSP_TRY(dev_alloc(ctx, (void**)&top, (size_t(1) << la) * 32));
+    LSP_TRY(dev_alloc(ctx, (void**)&top, (size_t(1) << la) * 32));
     for (int p = 0; p < n_points; p++) {
-        Fr* dst = la < log_m ? top : out[p];
-        LSP_LAUNCH(ctx, k_invden_top, unsigned(((size_t(1) << la) + 127) / 128), 128, 0, S + p, tw, log_m, la, dst);
-        if (la < log_m)
-            LSP_LAUNCH(ctx, k_invden_expand, unsigned(((size_t(1) << lb) + 127) / 128), 128, 0, S + p, tw, log_m, la, lb,
-                       (const Fr*)top, out[p]);
+        LSP_LAUNCH(ctx, k_invden_top, unsigned(((size_t(1) << la) + 127) / 128), 128, 0, S + p, tw, log_m, la, top);
+        if (direct) {
+            LSP_CUDA(ctx, cudaMemcpyAsync(out[p], top + p0, count * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            size_t n_nodes = count >> depth;
+            LSP_LAUNCH(ctx, k_invden_expand, unsigned((n_nodes + 127) / 128), 128, 0, S + p, tw, log_m, la, lb, (const Fr*)top, out[p],
+                       p0 >> depth, n_nodes);
+        }
     }
     dev_free(ctx, top);
     dev_free(ctx, S);
     return LSP_OK;
+}
+
+int inverse_denominators(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m, Fr* const* out) {
+    return inverse_denominators_range(ctx, z_dev, n_points, log_m, 0, size_t(1) << log_m, out);
 }
 
 // ===========================================================================
@@ -319,6 +332,8 @@ struct QuotientArgs {
     const Fr* tw_nq;      // omega_{Nq}^j, j < Nq/2
     const Fr* w_n_inv;    // omega_N^-1
     Fr* chunks;           // q columns of N
+    size_t p0, count;     // storage rows [p0, p0+count) handled by this launch; lde/inv_* are indexed by p - p_base
+    size_t p_base;        // storage row that lde[0] / inv_first[0] correspond to
 };
 
 __global__ void k_quotient_setup(int log_n, int log_q, Fr* __restrict__ zh, Fr* __restrict__ w_n_inv, Fr* __restrict__ pts) {
@@ -349,10 +364,12 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
     const Fr alpha_air = fr_load(A.publics), delta = fr_load(A.publics + 1), alpha = fr_load(A.alpha);
     const Fr w_n_inv = fr_load(A.w_n_inv);
     const Fr one = fr_one();
-    for (size_t p = blockIdx.x * size_t(blockDim.x) + threadIdx.x; p < nq; p += size_t(gridDim.x) * blockDim.x) {
-        const uint32_t i = bitrev32(uint32_t(p), lnq);
+    for (size_t pi = blockIdx.x * size_t(blockDim.x) + threadIdx.x; pi < A.count; pi += size_t(gridDim.x) * blockDim.x) {
+        const size_t pg = A.p0 + pi;                 // global storage row
+        const uint32_t i = bitrev32(uint32_t(pg), lnq);
         const uint32_t i_next = (i + q) & uint32_t(nq - 1);
-        const size_t pn = bitrev32(i_next, lnq);
+        const size_t p = pg - A.p_base;              // local row (next row lies in the same N-row block)
+        const size_t pn = size_t(bitrev32(i_next, lnq)) - A.p_base;
         const uint32_t c = i & (q - 1);
         // x = g * w_{Nq}^i
         Fr wi = (i < nq / 2) ? fr_load_nc(A.tw_nq + i) : fr_neg(fr_load_nc(A.tw_nq + (i - nq / 2)));
@@ -404,21 +421,25 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
     }
 }
 
-int quotient_permutation(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, int log_n, int log_q, const PermCfgDev& cfg,
-                         const Fr* publics_dev, const Fr* alpha_dev, Fr* chunks) {
+// Quotient values for storage rows [p0, p0+count) of the quotient domain (count a multiple of N:
+// whole chunks).  `lde` points at storage row p_base of every column (column stride lde_rows);
+// chunk c = bitrev(block) is written to chunks + c*N.
+int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, size_t p_base, int log_n, int log_q, const PermCfgDev& cfg,
+                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks) {
     int lnq = log_n + log_q;
     size_t nq = size_t(1) << lnq;
-    if (nq > lde_rows) return set_err(ctx, LSP_ERR_PARAM, "quotient domain (2^%d) exceeds the LDE (%zu rows)", lnq, lde_rows);
     if (lnq < 1) return set_err(ctx, LSP_ERR_PARAM, "trace of height 1 with a single quotient chunk is unsupported");
+    if (p0 + count > nq || (count & ((size_t(1) << log_n) - 1)) || (p0 & ((size_t(1) << log_n) - 1)))
+        return set_err(ctx, LSP_ERR_PARAM, "quotient range must cover whole chunks");
     Fr* scal = nullptr;  // zh[2q], w_n_inv, pts[2]
     size_t q = size_t(1) << log_q;
     LSP_TRY(dev_alloc(ctx, (void**)&scal, (2 * q + 3) * 32));
     Fr *zh = scal, *w_n_inv = scal + 2 * q, *pts = scal + 2 * q + 1;
     LSP_LAUNCH(ctx, k_quotient_setup, 1, unsigned(q < 32 ? 32 : q), 0, log_n, log_q, zh, w_n_inv, pts);
     Fr* inv[2] = {nullptr, nullptr};
-    LSP_TRY(dev_alloc(ctx, (void**)&inv[0], nq * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&inv[1], nq * 32));
-    LSP_TRY(inverse_denominators(ctx, pts, 2, lnq, inv));
+    LSP_TRY(dev_alloc(ctx, (void**)&inv[0], count * 32));
+    LSP_TRY(dev_alloc(ctx, (void**)&inv[1], count * 32));
+    LSP_TRY(inverse_denominators_range(ctx, pts, 2, lnq, p0, count, inv));
     const Fr* tw = nullptr;
     LSP_TRY(twiddles(ctx, lnq, false, &tw));
     QuotientArgs A;
@@ -429,17 +450,27 @@ int quotient_permutation(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, int log_n
     A.cfg = cfg;
     A.publics = publics_dev;
     A.alpha = alpha_dev;
-    A.inv_first = inv[0];
-    A.inv_last = inv[1];
+    A.inv_first = inv[0] - (p0 - p_base);  // indexed by local row p = pg - p_base
+    A.inv_last = inv[1] - (p0 - p_base);
     A.zh = zh;
     A.tw_nq = tw;
     A.w_n_inv = w_n_inv;
     A.chunks = chunks;
-    LSP_LAUNCH(ctx, k_quotient_permutation, grid_for(ctx, nq, 128), 128, 0, A);
+    A.p0 = p0;
+    A.count = count;
+    A.p_base = p_base;
+    LSP_LAUNCH(ctx, k_quotient_permutation, grid_for(ctx, count, 128), 128, 0, A);
     dev_free(ctx, inv[0]);
     dev_free(ctx, inv[1]);
     dev_free(ctx, scal);
     return LSP_OK;
+}
+
+int quotient_permutation(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, int log_n, int log_q, const PermCfgDev& cfg,
+                         const Fr* publics_dev, const Fr* alpha_dev, Fr* chunks) {
+    size_t nq = size_t(1) << (log_n + log_q);
+    if (nq > lde_rows) return set_err(ctx, LSP_ERR_PARAM, "quotient domain (2^%d) exceeds the LDE (%zu rows)", log_n + log_q, lde_rows);
+    return quotient_permutation_range(ctx, lde, lde_rows, 0, log_n, log_q, cfg, publics_dev, alpha_dev, 0, nq, chunks);
 }
 
 // ===========================================================================
@@ -540,23 +571,27 @@ int eval_columns_at(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, cons
 // written as  (lo+hi)/2 + t_j (lo-hi)  -> 2 multiplications per pair.
 // ===========================================================================
 __global__ void __launch_bounds__(128) k_fri_fold(const Fr* __restrict__ in, size_t h, int log_h, const Fr* __restrict__ beta,
-                                                  const Fr* __restrict__ tw_inv /* w_len^-e, e < len/2 */, Fr* __restrict__ out) {
+                                                  const Fr* __restrict__ tw_inv /* w_len^-e, e < len/2 */, Fr* __restrict__ out, size_t j0) {
+    // h = pairs handled here; j0 = global index of the first one; log_h = log2 of the GLOBAL pair count
     Fr half_beta = fr_halve(fr_load(beta));
     for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < h; j += size_t(gridDim.x) * blockDim.x) {
         Fr lo = fr_load_nc(in + 2 * j), hi = fr_load_nc(in + 2 * j + 1);
-        Fr t = fr_mul(half_beta, fr_load_nc(tw_inv + bitrev32(uint32_t(j), log_h)));
+        Fr t = fr_mul(half_beta, fr_load_nc(tw_inv + bitrev32(uint32_t(j0 + j), log_h)));
         Fr r = fr_add(fr_halve(fr_add(lo, hi)), fr_mul(t, fr_sub(lo, hi)));
         fr_store(out + j, r);
     }
 }
 
-int fri_fold(lsp_ctx* ctx, const Fr* in, size_t len, const Fr* beta_dev, Fr* out) {
-    size_t h = len / 2;
+// Folds the slice [2*j0, 2*j0 + 2*h_local) of a vector of global length `len`; `in`/`out` point at the slice.
+int fri_fold_range(lsp_ctx* ctx, const Fr* in, size_t len, size_t j0, size_t h_local, const Fr* beta_dev, Fr* out) {
     int log_len = ilog2(len);
     const Fr* tw = nullptr;
     LSP_TRY(twiddles(ctx, log_len, true, &tw));
-    LSP_LAUNCH(ctx, k_fri_fold, grid_for(ctx, h, 128), 128, 0, in, h, log_len - 1, beta_dev, tw, out);
+    LSP_LAUNCH(ctx, k_fri_fold, grid_for(ctx, h_local, 128), 128, 0, in, h_local, log_len - 1, beta_dev, tw, out, j0);
     return LSP_OK;
+}
+int fri_fold(lsp_ctx* ctx, const Fr* in, size_t len, const Fr* beta_dev, Fr* out) {
+    return fri_fold_range(ctx, in, len, 0, len / 2, beta_dev, out);
 }
 
 }  // namespace lsp

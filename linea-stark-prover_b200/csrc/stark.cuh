@@ -37,6 +37,8 @@ __device__ __forceinline__ uint32_t bitrev32(uint32_t x, int bits) { return bits
 int interpolate_columns(lsp_ctx* ctx, const Fr* in, size_t n, size_t width, Fr* coeffs);
 // shift_dev: device pointer to the coset shift (so that data-dependent shifts never visit the host)
 int coset_evaluate(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift_dev, Fr* out);
+int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift_dev, int block0,
+                          int n_blocks, Fr* out, size_t out_col_stride);
 
 // ---- core.cu ---------------------------------------------------------------
 int merkle_build(lsp_ctx* ctx, const Fr* const* d_cols, int width, size_t h, Fr* digests);
@@ -73,13 +75,19 @@ int upload_perm_cfgs(lsp_ctx* ctx, const lsp_perm_air_cfg* cfgs, int n_cfgs, siz
 
 // E[p] = 1/(g*w_L^{bitrev(p)} - z) for p < 2^log_m, one array per point (points in device memory)
 int inverse_denominators(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m, Fr* const* out);
+// same for rows [p0, p0+count) only (out[p] holds `count` entries)
+int inverse_denominators_range(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m, size_t p0, size_t count, Fr* const* out);
 
 int quotient_permutation(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, int log_n, int log_q, const PermCfgDev& cfg,
                          const Fr* publics_dev, const Fr* alpha_dev, Fr* chunks /* q columns of N */);
+
+int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, size_t p_base, int log_n, int log_q, const PermCfgDev& cfg,
+                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks);
 
 // y[c] = sum_k coeffs[c][k] * z^k
 int eval_columns_at(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, const Fr* z_dev, Fr* y_dev);
 
 int fri_fold(lsp_ctx* ctx, const Fr* in, size_t len, const Fr* beta_dev, Fr* out);
+int fri_fold_range(lsp_ctx* ctx, const Fr* in, size_t len, size_t j0, size_t h_local, const Fr* beta_dev, Fr* out);
 
 }  // namespace lsp

@@ -69,6 +69,12 @@ SIGNATURES = {
                                         C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
     "lsp_prove_permutation_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(PermAirCfg), C.c_int, u64p,
                                             u64p, C.c_size_t, f32p]),
+    "lsp_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
+    "lsp_comm_init_nccl": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(vp)]),
+    "lsp_comm_init_local": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
+    "lsp_comm_destroy": (None, [vp]),
+    "lsp_prove_permutation_sharded": (C.c_int, [vp, C.POINTER(FriConfig), u64p, C.c_size_t, C.c_size_t,
+                                                C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
 }
 
 _lib = None

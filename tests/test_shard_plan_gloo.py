@@ -1,0 +1,83 @@
+"""The N>1 host logic on CPU: world_size-2 gloo processes each take their shard of the LDE
+(shard_plan), build their Merkle subtree and fold their FRI slice with the ORACLE, exchange
+subtree roots with all_gather, and must reproduce the unsharded commitment and fold."""
+import os
+import sys
+from pathlib import Path
+
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import __graft_entry__ as g
+    from oracle import dft as OD
+    from oracle import field as F
+    from oracle import merkle as OM
+    from oracle import poseidon2 as OP
+    from oracle import stark as OS
+    pkg = g.load_package()
+    p = OP.Poseidon2Params.from_seed(1)
+    log_n, blow = 3, 2
+    rng = F.SplitMix64(4)
+    mat = [[rng.next_fr() for _ in range(3)] for _ in range(1 << log_n)]
+    plan = pkg.shard_plan(log_n, blow, world, rank)
+    # this rank's rows of the bit-reversed LDE = its cosets, each a size-N coset evaluation
+    n = 1 << log_n
+    w_l = F.two_adic_generator(log_n + blow)
+    local = []
+    for c in plan["cosets"]:
+        block = OD.coset_lde_batch(mat, 0, F.GENERATOR * pow(w_l, c, F.R_MOD) % F.R_MOD)
+        local += block
+    full = OD.coset_lde_batch(mat, blow, F.GENERATOR)
+    assert local == full[plan["row0"]:plan["row0"] + plan["rows"]]
+    sub = OM.MerkleTree(p, [local])
+    roots = [None] * world
+    dist.all_gather_object(roots, sub.root)
+    top = roots
+    while len(top) > 1:
+        top = [OP.compress(p, top[2 * i], top[2 * i + 1]) for i in range(len(top) // 2)]
+    assert top[0] == OM.MerkleTree(p, [full]).root
+    # FRI fold of the local slice equals the slice of the global fold
+    vec = [r[0] for r in full]
+    beta = rng.next_fr()
+    gfold = OS.fold_matrix(beta, [[vec[2 * j], vec[2 * j + 1]] for j in range(len(vec) // 2)])
+    h = len(vec) // 2
+    log_h = h.bit_length() - 1
+    g_inv = F.inv(F.two_adic_generator(log_h + 1))
+    j0 = plan["row0"] // 2
+    mine = []
+    for j in range(plan["rows"] // 2):
+        t = F.halve(beta) * pow(g_inv, F.reverse_bits_len(j0 + j, log_h), F.R_MOD) % F.R_MOD
+        lo, hi = vec[2 * (j0 + j)], vec[2 * (j0 + j) + 1]
+        mine.append((F.halve((lo + hi) % F.R_MOD) + t * (lo - hi)) % F.R_MOD)
+    assert mine == gfold[j0:j0 + plan["rows"] // 2]
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put(rank)
+
+
+def test_shard_plan_world2_gloo():
+    world, port = 2, 29531
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    assert sorted(q.get() for _ in range(world)) == [0, 1]
+
+
+def test_shard_plan_shapes(pkg):
+    import pytest
+    assert pkg.shard_plan(19, 3, 8, 3) == dict(row0=3 << 19, rows=1 << 19, blocks=[3], cosets=[6])
+    assert pkg.shard_plan(4, 3, 2, 1)["cosets"] == [1, 5, 3, 7]
+    with pytest.raises(pkg.BackendError):
+        pkg.shard_plan(4, 1, 4, 0)
