@@ -178,6 +178,10 @@ void lsp_comm_destroy(lsp_comm* comm);
 int lsp_prove_permutation_sharded(lsp_comm* comm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows,
                                   size_t width, const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
                                   uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+/* Same, for a trace every rank has already uploaded with lsp_mat_upload / lsp_permutation_trace. */
+int lsp_prove_permutation_sharded_dev(lsp_comm* comm, const lsp_fri_config* fri, const lsp_mat* trace,
+                                      const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                                      uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
 
 #ifdef __cplusplus
 }

@@ -456,7 +456,9 @@ def prove_sharded(comm: Comm, fri: FriConfig, cfgs, trace, publics, timings=None
     arr, keep = _c_cfgs(cfgs)
     pub = to_mont_array(publics)
     tm = np.zeros(8, dtype=np.float32)
-    if isinstance(trace, tuple):
+    if isinstance(trace, Mat):
+        n, w = trace.height, trace.width
+    elif isinstance(trace, tuple):
         limbs, n, w = trace
     else:
         n, w = len(trace), len(trace[0])
@@ -468,8 +470,12 @@ def prove_sharded(comm: Comm, fri: FriConfig, cfgs, trace, publics, timings=None
     if words == 0:
         raise BackendError("unsupported FRI parameters for this trace height")
     out = np.empty(words, dtype=np.uint64)
-    rc = ctx.lib.lsp_prove_permutation_sharded(comm.h, C.byref(cf), ffi.as_u64p(limbs), n, w, arr, len(cfgs),
-                                               ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    if isinstance(trace, Mat):
+        rc = ctx.lib.lsp_prove_permutation_sharded_dev(comm.h, C.byref(cf), trace.h, arr, len(cfgs), ffi.as_u64p(pub),
+                                                       ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    else:
+        rc = ctx.lib.lsp_prove_permutation_sharded(comm.h, C.byref(cf), ffi.as_u64p(limbs), n, w, arr, len(cfgs),
+                                                   ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
     ctx.check(rc, "lsp_prove_permutation_sharded")
     if timings is not None:
         timings.update({k: float(v) for k, v in zip(STAGE_NAMES, tm)})

@@ -1,4 +1,7 @@
-// Carry-free Montgomery product for BLS12-377 Fr on 9 x 29-bit limbs (candidate core).
+// Carry-free Montgomery product for BLS12-377 Fr on 9 x 29-bit limbs -- MEASURED ALTERNATIVE, not
+// on the product path (tools/mulbench.cu, tools/permlat.cu): 45-47 G modmul/s against 57 G for the
+// carry-chained 8 x 32-bit product of fr.cuh, and 1303 vs 997 cycles for a lone warp, because the
+// ~180 shift/mask/carry instructions it adds cost as much issue time as the carries it removes.
 //
 // Every 29x29-bit product is < 2^58, so the 17 column accumulators of a 9x9 schoolbook
 // product plus the 9x8 reduction products stay below 2^63: no carry flag is ever needed

@@ -75,6 +75,8 @@ SIGNATURES = {
     "lsp_comm_destroy": (None, [vp]),
     "lsp_prove_permutation_sharded": (C.c_int, [vp, C.POINTER(FriConfig), u64p, C.c_size_t, C.c_size_t,
                                                 C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
+    "lsp_prove_permutation_sharded_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(PermAirCfg), C.c_int, u64p, u64p,
+                                                    C.c_size_t, f32p]),
 }
 
 _lib = None

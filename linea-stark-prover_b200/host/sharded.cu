@@ -413,13 +413,13 @@ extern "C" void lsp_comm_destroy(lsp_comm* cm) {
     delete cm;
 }
 
-extern "C" int lsp_prove_permutation_sharded(lsp_comm* cm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
-                                             const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out,
-                                             size_t proof_words, float* timings_ms_out) {
-    if (!cm || !fri || !trace || !cfgs || !publics || !proof_out) return LSP_ERR_PARAM;
+extern "C" int lsp_prove_permutation_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri, const lsp_mat* tr, const lsp_perm_air_cfg* cfgs,
+                                                 int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words,
+                                                 float* timings_ms_out) {
+    if (!cm || !fri || !tr || !cfgs || !publics || !proof_out) return LSP_ERR_PARAM;
     lsp_ctx* ctx = cm->ctx;
     if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
-    const size_t n = rows, W = width;
+    const size_t n = tr->rows, W = tr->width;
     if (!is_pow2(n)) return set_err(ctx, LSP_ERR_PARAM, "trace height %zu is not a power of two (prove would panic)", n);
     const int G = cm->world, log_g = ilog2(size_t(G));
     const int log_n = ilog2(n), log_q = 1, q = 2;
@@ -464,13 +464,6 @@ extern "C" int lsp_prove_permutation_sharded(lsp_comm* cm, const lsp_fri_config*
     } ev_guard{ev};
 
     // ---- replicated inputs: trace, coefficients, AIR config ---------------------------------------
-    lsp_mat* tr = nullptr;
-    LSP_TRY(lsp_mat_upload(ctx, trace, n, W, &tr));
-    struct MatGuard {
-        lsp_ctx* c;
-        lsp_mat* m;
-        ~MatGuard() { lsp_mat_free(c, m); }
-    } tr_guard{ctx, tr};
     PermCfgDev cfg_dev;
     void* cfg_blob = nullptr;
     LSP_TRY(upload_perm_cfgs(ctx, cfgs, n_cfgs, W, &cfg_dev, &cfg_blob));
@@ -745,4 +738,15 @@ extern "C" int lsp_prove_permutation_sharded(lsp_comm* cm, const lsp_fri_config*
     if (timings_ms_out)
         for (int i = 0; i < 8; i++) cudaEventElapsedTime(&timings_ms_out[i], ev[i], ev[i + 1]);
     return LSP_OK;
+}
+
+extern "C" int lsp_prove_permutation_sharded(lsp_comm* cm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
+                                             const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out,
+                                             size_t proof_words, float* timings_ms_out) {
+    if (!cm || !trace) return LSP_ERR_PARAM;
+    lsp_mat* m = nullptr;
+    LSP_TRY(lsp_mat_upload(cm->ctx, trace, rows, width, &m));
+    int rc = lsp_prove_permutation_sharded_dev(cm, fri, m, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
+    lsp_mat_free(cm->ctx, m);
+    return rc;
 }
