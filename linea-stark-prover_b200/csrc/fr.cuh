@@ -167,8 +167,13 @@ __device__ __forceinline__ Fr fr_halve(const Fr& a) {
 }
 
 // ---- Montgomery product ---------------------------------------------------
+// Cost model measured on B200 (profiles/r1*_k_leaf_hash, tools/pipe_probe.cu): every 32x32->64
+// product occupies the FMA-heavy pipe for 4 cycles per warp as one IMAD.WIDE.U32(.X), or 6 as an
+// IMAD (lo) + IMAD.HI pair; IADD3/SHF/SEL go to the ALU pipe.  So the kernels here are bound by
+// the NUMBER OF IMAD.WIDE: a product is 64 (a*b) + 56 (m*p: p[0] = 1 needs no multiply) = 120,
+// a square 36 + 56 = 92.
 // lane (lo,hi) = x*y                       (no carries)
-#define LSP_MULW(lo, hi, x, y) asm("mul.lo.u32 %0, %2, %3;\n\tmul.hi.u32 %1, %2, %3;" : "=r"(lo), "=r"(hi) : "r"(x), "r"(y))
+#define LSP_MULW(lo, hi, x, y) asm("{.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0,%1}, t;}" : "=r"(lo), "=r"(hi) : "r"(x), "r"(y))
 // first lane of a chain: (lo,hi) += x*y, sets CC
 #define LSP_MADW_CC(lo, hi, x, y) asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(x), "r"(y))
 // middle lane: (lo,hi) += x*y + CC, sets CC
@@ -176,66 +181,67 @@ __device__ __forceinline__ Fr fr_halve(const Fr& a) {
 // shifted variants: (lo,hi) = x*y + (ilo,ihi) [+ CC], sets CC
 #define LSP_MADW3_CC(lo, hi, x, y, ilo, ihi) asm volatile("mad.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;" : "=r"(lo), "=r"(hi) : "r"(x), "r"(y), "r"(ilo), "r"(ihi))
 #define LSP_MADWC3_CC(lo, hi, x, y, ilo, ihi) asm volatile("madc.lo.cc.u32 %0, %2, %3, %4;\n\tmadc.hi.cc.u32 %1, %2, %3, %5;" : "=r"(lo), "=r"(hi) : "r"(x), "r"(y), "r"(ilo), "r"(ihi))
+// (lo,hi) = (ilo,ihi) + CC, sets CC   (a lane that receives no product this step)
+#define LSP_COPYC_CC(lo, hi, ilo, ihi) asm volatile("addc.cc.u32 %0, %2, 0;\n\taddc.cc.u32 %1, %3, 0;" : "=r"(lo), "=r"(hi) : "r"(ilo), "r"(ihi))
 #define LSP_ADDC0(x) asm volatile("addc.u32 %0, %0, 0;" : "+r"(x))
 
-// One word-serial step on (X aligned at 2^0, Y aligned at 2^32).
-//   FIRST: X = a_even*bi, Y = a_odd*bi.
-//   else : the previous step left X_old[0] == 0; divide by 2^32 by renaming
-//          (new X = old Y, new Y = old X >> 64, stray limb X_old[1] joins
-//          new X[0]) while adding a*bi; then add m*p with m = -X[0].
-// Caller passes the arrays already swapped: X = old Y, Z = old X.
-template <bool FIRST>
-__device__ __forceinline__ void mont_step(uint32_t* X, uint32_t* Y, const uint32_t* Z, const uint32_t* a, uint32_t bi) {
-    if (FIRST) {
-        LSP_MULW(X[0], X[1], a[0], bi);
-        LSP_MULW(X[2], X[3], a[2], bi);
-        LSP_MULW(X[4], X[5], a[4], bi);
-        LSP_MULW(X[6], X[7], a[6], bi);
-        LSP_MULW(Y[0], Y[1], a[1], bi);
-        LSP_MULW(Y[2], Y[3], a[3], bi);
-        LSP_MULW(Y[4], Y[5], a[5], bi);
-        LSP_MULW(Y[6], Y[7], a[7], bi);
-    } else {
-        // stray limb, carry feeds the Y chain (weight 2^32)
-        asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(X[0]) : "r"(Z[1]));
-        LSP_MADWC3_CC(Y[0], Y[1], a[1], bi, Z[2], Z[3]);
-        LSP_MADWC3_CC(Y[2], Y[3], a[3], bi, Z[4], Z[5]);
-        LSP_MADWC3_CC(Y[4], Y[5], a[5], bi, Z[6], Z[7]);
-        asm volatile("madc.lo.cc.u32 %0, %2, %3, 0;\n\tmadc.hi.u32 %1, %2, %3, 0;" : "=r"(Y[6]), "=r"(Y[7]) : "r"(a[7]), "r"(bi));
-        LSP_MADW_CC(X[0], X[1], a[0], bi);
-        LSP_MADWC_CC(X[2], X[3], a[2], bi);
-        LSP_MADWC_CC(X[4], X[5], a[4], bi);
-        LSP_MADWC_CC(X[6], X[7], a[6], bi);
-        LSP_ADDC0(Y[7]);
-    }
-    uint32_t m = 0u - X[0];
-    const uint32_t p0 = LSP_P0, p1 = LSP_P1, p2 = LSP_P2, p3 = LSP_P3, p4 = LSP_P4, p5 = LSP_P5, p6 = LSP_P6, p7 = LSP_P7;
+// The two accumulators of the word-serial product: X holds the limbs aligned at 2^0, Y those
+// aligned at 2^32, so every 32x32->64 product lands on a 64-bit lane (an even/odd register pair)
+// and ptxas emits one IMAD.WIDE.U32(.X) per product with the carry in a predicate.
+//
+// Reduction half of a step: m = -X[0] (-r^{-1} mod 2^32 = 0xffffffff for this modulus), then
+// X + 2^32 Y += m * p, which clears X[0].  m comes out of an asm statement on purpose: when ptxas
+// sees m = -X[0] it rewrites m*p_i as X[0]*(-p_i) and then splits every one of these lanes into
+// IMAD + IMAD.HI.U32 (6 pipe cycles instead of 4).  p[0] = 1: that lane is an addition.
+__device__ __forceinline__ void mont_reduce_step(uint32_t* X, uint32_t* Y) {
+    uint32_t m;
+    asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(X[0]));
+    const uint32_t p1 = LSP_P1, p2 = LSP_P2, p3 = LSP_P3, p4 = LSP_P4, p5 = LSP_P5, p6 = LSP_P6, p7 = LSP_P7;
     LSP_MADW_CC(Y[0], Y[1], p1, m);
     LSP_MADWC_CC(Y[2], Y[3], p3, m);
     LSP_MADWC_CC(Y[4], Y[5], p5, m);
     LSP_MADWC_CC(Y[6], Y[7], p7, m);
-    LSP_MADW_CC(X[0], X[1], p0, m);
+    asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.cc.u32 %1, %1, 0;" : "+r"(X[0]), "+r"(X[1]) : "r"(m));
     LSP_MADWC_CC(X[2], X[3], p2, m);
     LSP_MADWC_CC(X[4], X[5], p4, m);
     LSP_MADWC_CC(X[6], X[7], p6, m);
     LSP_ADDC0(Y[7]);
 }
 
-// Montgomery product, result in [0, 2r) provided a < 2^255 (b arbitrary < 2^256)
-// and a*b < 2^256 * r  (true for a, b < 3r).
-__device__ __forceinline__ Fr fr_mul_lazy(const Fr& a, const Fr& b) {
-    uint32_t E[8], O[8];
-    mont_step<true>(E, O, nullptr, a.l, b.l[0]);
-    // after step k the accumulator with X[0]==0 is the one passed as X
-    uint32_t E2[8], O2[8];
-    mont_step<false>(O, E2, E, a.l, b.l[1]);   // X=O, new Y=E2 from old X=E
-    mont_step<false>(E2, O2, O, a.l, b.l[2]);
-    mont_step<false>(O2, E, E2, a.l, b.l[3]);
-    mont_step<false>(E, O, O2, a.l, b.l[4]);
-    mont_step<false>(O, E2, E, a.l, b.l[5]);
-    mont_step<false>(E2, O2, O, a.l, b.l[6]);
-    mont_step<false>(O2, E, E2, a.l, b.l[7]);
-    // T = X + Y*2^32 with X = O2 (X[0] == 0), Y = E.  result = T / 2^32.
+// Product half of a step on (X aligned at 2^0, Y aligned at 2^32): adds v * s where lane j of v
+// has weight 2^(32 j); lanes below FROM are absent (squaring rows).
+//   FIRST: X = v_even*s, Y = v_odd*s.
+//   else : the previous step left X_old[0] == 0; divide by 2^32 by renaming (new X = old Y,
+//          new Y = old X >> 64, stray limb X_old[1] joins new X[0]) while adding v*s.
+// Caller passes the arrays already swapped: X = old Y, Z = old X.
+template <bool FIRST, int FROM>
+__device__ __forceinline__ void mont_row(uint32_t* X, uint32_t* Y, const uint32_t* Z, const uint32_t* v, uint32_t s) {
+    if (FIRST) {
+        LSP_MULW(X[0], X[1], v[0], s);
+        LSP_MULW(X[2], X[3], v[2], s);
+        LSP_MULW(X[4], X[5], v[4], s);
+        LSP_MULW(X[6], X[7], v[6], s);
+        LSP_MULW(Y[0], Y[1], v[1], s);
+        LSP_MULW(Y[2], Y[3], v[3], s);
+        LSP_MULW(Y[4], Y[5], v[5], s);
+        LSP_MULW(Y[6], Y[7], v[7], s);
+    } else {
+        // stray limb, carry feeds the Y chain (weight 2^32)
+        asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(X[0]) : "r"(Z[1]));
+        if (1 >= FROM) LSP_MADWC3_CC(Y[0], Y[1], v[1], s, Z[2], Z[3]); else LSP_COPYC_CC(Y[0], Y[1], Z[2], Z[3]);
+        if (3 >= FROM) LSP_MADWC3_CC(Y[2], Y[3], v[3], s, Z[4], Z[5]); else LSP_COPYC_CC(Y[2], Y[3], Z[4], Z[5]);
+        if (5 >= FROM) LSP_MADWC3_CC(Y[4], Y[5], v[5], s, Z[6], Z[7]); else LSP_COPYC_CC(Y[4], Y[5], Z[6], Z[7]);
+        asm volatile("madc.lo.cc.u32 %0, %2, %3, 0;\n\tmadc.hi.u32 %1, %2, %3, 0;" : "=r"(Y[6]), "=r"(Y[7]) : "r"(v[7]), "r"(s));
+        if (0 >= FROM) LSP_MADW_CC(X[0], X[1], v[0], s);
+        if (2 >= FROM) { if (2 >= FROM && 0 < FROM) LSP_MADW_CC(X[2], X[3], v[2], s); else LSP_MADWC_CC(X[2], X[3], v[2], s); }
+        if (4 >= FROM) { if (2 < FROM) LSP_MADW_CC(X[4], X[5], v[4], s); else LSP_MADWC_CC(X[4], X[5], v[4], s); }
+        if (6 >= FROM) { if (4 < FROM) LSP_MADW_CC(X[6], X[7], v[6], s); else LSP_MADWC_CC(X[6], X[7], v[6], s); }
+        if (6 >= FROM) LSP_ADDC0(Y[7]);
+    }
+}
+
+// T = X + Y*2^32 with X[0] == 0; result = T / 2^32.
+__device__ __forceinline__ Fr mont_finish(const uint32_t* X, const uint32_t* Y) {
     Fr r;
     asm volatile("add.cc.u32 %0, %8, %16;\n\t"
         "addc.cc.u32 %1, %9, %17;\n\t"
@@ -246,9 +252,72 @@ __device__ __forceinline__ Fr fr_mul_lazy(const Fr& a, const Fr& b) {
         "addc.cc.u32 %6, %14, %22;\n\t"
         "addc.u32 %7, %15, 0;"
         : "=r"(r.l[0]), "=r"(r.l[1]), "=r"(r.l[2]), "=r"(r.l[3]), "=r"(r.l[4]), "=r"(r.l[5]), "=r"(r.l[6]), "=r"(r.l[7])
-        : "r"(E[0]), "r"(E[1]), "r"(E[2]), "r"(E[3]), "r"(E[4]), "r"(E[5]), "r"(E[6]), "r"(E[7]),
-          "r"(O2[1]), "r"(O2[2]), "r"(O2[3]), "r"(O2[4]), "r"(O2[5]), "r"(O2[6]), "r"(O2[7]));
+        : "r"(Y[0]), "r"(Y[1]), "r"(Y[2]), "r"(Y[3]), "r"(Y[4]), "r"(Y[5]), "r"(Y[6]), "r"(Y[7]),
+          "r"(X[1]), "r"(X[2]), "r"(X[3]), "r"(X[4]), "r"(X[5]), "r"(X[6]), "r"(X[7]));
     return r;
+}
+
+// Montgomery product, result in [0, 2r) provided a < 2^255 (b arbitrary < 2^256)
+// and a*b < 2^256 * r  (true for a, b < 3r).
+__device__ __forceinline__ Fr fr_mul_lazy(const Fr& a, const Fr& b) {
+    uint32_t E[8], O[8], E2[8], O2[8];
+    mont_row<true, 0>(E, O, nullptr, a.l, b.l[0]);
+    mont_reduce_step(E, O);
+    // after step k the accumulator with X[0]==0 is the one passed as X
+    mont_row<false, 0>(O, E2, E, a.l, b.l[1]);   // X=O, new Y=E2 from old X=E
+    mont_reduce_step(O, E2);
+    mont_row<false, 0>(E2, O2, O, a.l, b.l[2]);
+    mont_reduce_step(E2, O2);
+    mont_row<false, 0>(O2, E, E2, a.l, b.l[3]);
+    mont_reduce_step(O2, E);
+    mont_row<false, 0>(E, O, O2, a.l, b.l[4]);
+    mont_reduce_step(E, O);
+    mont_row<false, 0>(O, E2, E, a.l, b.l[5]);
+    mont_reduce_step(O, E2);
+    mont_row<false, 0>(E2, O2, O, a.l, b.l[6]);
+    mont_reduce_step(E2, O2);
+    mont_row<false, 0>(O2, E, E2, a.l, b.l[7]);
+    mont_reduce_step(O2, E);
+    return mont_finish(O2, E);
+}
+
+// Montgomery square, result in [0, 2r) for a < 2^253.  Row k adds a_k * (a_k 2^(32k) +
+// 2 * sum_{j>k} a_j 2^(32j)): the doubled tail is read from the limbs of 2a (which fits 8 limbs),
+// except that its lowest limb drops the bit shifted in from a_k.  36 products instead of 64; every
+// column is complete by the time its reduction step runs because row k only touches columns >= 2k.
+template <int K>
+__device__ __forceinline__ void sqr_row(uint32_t* X, uint32_t* Y, const uint32_t* Z, const Fr& a, const uint32_t* sh, const uint32_t* db) {
+    uint32_t v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = j == K ? a.l[j] : (j == K + 1 ? sh[j] : db[j]);
+    mont_row<K == 0, K>(X, Y, Z, v, a.l[K]);
+}
+__device__ __forceinline__ Fr fr_sqr_lazy(const Fr& a) {
+    uint32_t sh[8], db[8];
+    sh[0] = db[0] = 0;
+#pragma unroll
+    for (int j = 1; j < 8; j++) {
+        sh[j] = a.l[j] << 1;
+        db[j] = __funnelshift_l(a.l[j - 1], a.l[j], 1);
+    }
+    uint32_t E[8], O[8], E2[8], O2[8];
+    sqr_row<0>(E, O, nullptr, a, sh, db);
+    mont_reduce_step(E, O);
+    sqr_row<1>(O, E2, E, a, sh, db);
+    mont_reduce_step(O, E2);
+    sqr_row<2>(E2, O2, O, a, sh, db);
+    mont_reduce_step(E2, O2);
+    sqr_row<3>(O2, E, E2, a, sh, db);
+    mont_reduce_step(O2, E);
+    sqr_row<4>(E, O, O2, a, sh, db);
+    mont_reduce_step(E, O);
+    sqr_row<5>(O, E2, E, a, sh, db);
+    mont_reduce_step(O, E2);
+    sqr_row<6>(E2, O2, O, a, sh, db);
+    mont_reduce_step(E2, O2);
+    sqr_row<7>(O2, E, E2, a, sh, db);
+    mont_reduce_step(O2, E);
+    return mont_finish(O2, E);
 }
 
 __device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
@@ -256,7 +325,11 @@ __device__ __forceinline__ Fr fr_mul(const Fr& a, const Fr& b) {
     fr_reduce_once(r);
     return r;
 }
-__device__ __forceinline__ Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
+__device__ __forceinline__ Fr fr_sqr(const Fr& a) {
+    Fr r = fr_sqr_lazy(a);
+    fr_reduce_once(r);
+    return r;
+}
 
 // Out-of-line product (arguments and result travel in registers, ~20 MOVs per call).
 // Used where many products follow each other (Poseidon2 S-boxes, exponentiations): one
@@ -264,7 +337,7 @@ __device__ __forceinline__ Fr fr_sqr(const Fr& a) { return fr_mul(a, a); }
 // with the product inlined a Poseidon2 permutation is ~84 KiB of straight-line code and
 // the leaf-hash kernel stalls on instruction fetch (profiles/r1a: stall_no_instruction).
 static __device__ __noinline__ Fr fr_mul_call(Fr a, Fr b) { return fr_mul(a, b); }
-__device__ __forceinline__ Fr fr_sqr_call(const Fr& a) { return fr_mul_call(a, a); }
+static __device__ __noinline__ Fr fr_sqr_call(Fr a) { return fr_sqr(a); }
 
 // a^e for a small runtime exponent (e < 2^32)
 __device__ __forceinline__ Fr fr_pow_u32(Fr a, uint32_t e) {

@@ -6,12 +6,14 @@
 #include <cuda_runtime.h>
 #include "fr.cuh"
 #include "fr29.cuh"
+#include "fr_mul_v1.cuh"
 
 using namespace lsp;
 #define CHAINS 2
 #define ITERS 512
 
-// MODE 0: fr_mul (canonical)  1: fr_mul_lazy  2: f29 packed in/out per mul  3: f29 persistent (sqr/mul chain)
+// MODE 0: fr_mul_v1 (round-1a product)  1: fr_mul  2: f29 packed in/out per mul  3: f29 persistent
+// MODE 4: x = x*x with fr_mul_v1  5: x = fr_sqr(x)  6: x = y*x then x = x^2 (S-box-like mix)
 template <int MODE>
 __global__ void __launch_bounds__(128) k(const Fr* __restrict__ in, Fr* __restrict__ out, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -32,12 +34,14 @@ __global__ void __launch_bounds__(128) k(const Fr* __restrict__ in, Fr* __restri
         for (int it = 0; it < ITERS; it++) {
 #pragma unroll
             for (int c = 0; c < CHAINS; c++) {
-                if (MODE == 0) x[c] = fr_mul(x[c], y[c]);
-                if (MODE == 1) x[c] = fr_mul_lazy(x[c], y[c]);
+                if (MODE == 0) x[c] = lsp_v1::fr_mul_v1(x[c], y[c]);
+                if (MODE == 1) x[c] = fr_mul(x[c], y[c]);
+                if (MODE == 4) x[c] = lsp_v1::fr_mul_v1(x[c], x[c]);
+                if (MODE == 5) x[c] = fr_sqr(x[c]);
                 if (MODE == 2) x[c] = f29_pack_lazy(f29_mul(f29_unpack(x[c]), f29_unpack(y[c])));
             }
         }
-        if (MODE != 0) {
+        if (MODE == 2) {
 #pragma unroll
             for (int c = 0; c < CHAINS; c++) fr_reduce_once(x[c]);
         }
@@ -78,21 +82,25 @@ int main() {
     size_t out_n = size_t(blocks) * 128 * CHAINS;
     cudaMalloc(&in, n * sizeof(Fr)); cudaMalloc(&o0, out_n * sizeof(Fr)); cudaMalloc(&o1, out_n * sizeof(Fr));
     cudaMemcpy(in, h, n * sizeof(Fr), cudaMemcpyHostToDevice);
-    run<0>("fr_mul (32-bit chains)", in, o0, n, blocks);
-    run<1>("fr_mul_lazy", in, o1, n, blocks);
+    run<0>("fr_mul_v1 (round 1a)", in, o0, n, blocks);
+    run<1>("fr_mul (120 IMAD.WIDE)", in, o1, n, blocks);
     Fr* a = (Fr*)malloc(out_n * sizeof(Fr)); Fr* b = (Fr*)malloc(out_n * sizeof(Fr));
     cudaMemcpy(a, o0, out_n * sizeof(Fr), cudaMemcpyDeviceToHost);
     auto check = [&](const char* nm, Fr* dev) {
         cudaMemcpy(b, dev, out_n * sizeof(Fr), cudaMemcpyDeviceToHost);
         size_t bad = 0;
         for (size_t i = 0; i < out_n; i++) if (memcmp(&a[i], &b[i], 32)) bad++;
-        printf("   %s vs fr_mul: %zu mismatches of %zu\n", nm, bad, out_n);
+        printf("   %s vs v1: %zu mismatches of %zu\n", nm, bad, out_n);
     };
-    check("lazy", o1);
+    check("fr_mul", o1);
     run<2>("f29 unpack/mul/pack", in, o1, n, blocks);
     check("f29 packed", o1);
     run<3>("f29 persistent", in, o1, n, blocks);
     check("f29 persistent", o1);
+    run<4>("v1 x*x chain", in, o0, n, blocks);
+    cudaMemcpy(a, o0, out_n * sizeof(Fr), cudaMemcpyDeviceToHost);
+    run<5>("fr_sqr (92 IMAD.WIDE)", in, o1, n, blocks);
+    check("fr_sqr", o1);
     printf("status: %s\n", cudaGetErrorString(cudaDeviceSynchronize()));
     return 0;
 }
