@@ -42,9 +42,10 @@ __global__ void __launch_bounds__(256) k_cm_to_rm(const Fr* __restrict__ cm, Fr*
 template <int D>
 __global__ void __launch_bounds__(128) k_p2_permute(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
                                                     Fr* __restrict__ out, size_t n) {
+    LSP_P2_SLOT_DECL(128);
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
         Fr s0 = fr_load(in + 3 * i), s1 = fr_load(in + 3 * i + 1), s2 = fr_load(in + 3 * i + 2);
-        p2_permute<D>(P, s0, s1, s2);
+        p2_permute<D, 128>(P, s0, s1, s2, LSP_P2_SLOT(128));
         fr_store(out + 3 * i, s0);
         fr_store(out + 3 * i + 1, s1);
         fr_store(out + 3 * i + 2, s2);
@@ -54,20 +55,19 @@ __global__ void __launch_bounds__(128) k_p2_permute(const __grid_constant__ P2Pa
 // Leaf digests: one thread per row.  PaddingFreeSponge<Perm,3,2,1>::hash_iter over
 // the concatenation of that row in every matrix (overwrite mode, rate 2).
 // cols[] are column base pointers (column-major storage => coalesced across rows).
+// The permutation is inlined at ONE site (odd tail folded into the loop): the kernel stays
+// inside the instruction cache.
 template <int D>
-__global__ void __launch_bounds__(128, 8) k_leaf_hash(const __grid_constant__ P2Params P, const Fr* const* __restrict__ cols,
+__global__ void __launch_bounds__(128, 6) k_leaf_hash(const __grid_constant__ P2Params P, const Fr* const* __restrict__ cols,
                                                    int width, size_t rows, Fr* __restrict__ digests) {
+    LSP_P2_SLOT_DECL(128);
     for (size_t r = blockIdx.x * size_t(blockDim.x) + threadIdx.x; r < rows; r += size_t(gridDim.x) * blockDim.x) {
         Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
-        int c = 0;
-        for (; c + 1 < width; c += 2) {
+#pragma unroll 1
+        for (int c = 0; c < width; c += 2) {
             s0 = fr_load_nc(cols[c] + r);
-            s1 = fr_load_nc(cols[c + 1] + r);
-            p2_permute<D>(P, s0, s1, s2);
-        }
-        if (c < width) {  // odd tail: state[1] keeps its stale value
-            s0 = fr_load_nc(cols[c] + r);
-            p2_permute<D>(P, s0, s1, s2);
+            if (c + 1 < width) s1 = fr_load_nc(cols[c + 1] + r);  // odd tail: state[1] keeps its stale value
+            p2_permute<D, 128>(P, s0, s1, s2, LSP_P2_SLOT(128));
         }
         fr_store(digests + r, s0);
     }
@@ -75,12 +75,28 @@ __global__ void __launch_bounds__(128, 8) k_leaf_hash(const __grid_constant__ P2
 
 // One Merkle layer: out[i] = compress(in[2i], in[2i+1]).
 template <int D>
-__global__ void __launch_bounds__(128, 8) k_compress_layer(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
+__global__ void __launch_bounds__(128, 6) k_compress_layer(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
                                                         Fr* __restrict__ out, size_t n_out) {
+    LSP_P2_SLOT_DECL(128);
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n_out; i += size_t(gridDim.x) * blockDim.x) {
         Fr l = fr_load(in + 2 * i), r = fr_load(in + 2 * i + 1);
-        fr_store(out + i, p2_compress<D>(P, l, r));
+        fr_store(out + i, p2_compress<D, 128>(P, l, r, LSP_P2_SLOT(128)));
     }
+}
+
+// The same layer for the small tops of the trees, where the cost is the latency of one
+// permutation: three lanes per node (p2_permute_tri), one warp per block so that the warps
+// spread over the SM sub-partitions.  Lane 3k+w of a warp holds word w of node warp*10+k.
+template <int D>
+__global__ void __launch_bounds__(32) k_compress_layer_tri(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
+                                                           Fr* __restrict__ out, size_t n_out) {
+    const int lane = threadIdx.x, k = lane / 3, w = lane - 3 * k;
+    size_t i = size_t(blockIdx.x) * 10 + k;
+    const bool live = k < 10 && i < n_out;
+    if (!live) i = 0;
+    Fr s = w < 2 ? fr_load(in + 2 * i + w) : fr_zero();
+    p2_permute_tri<D>(P, s, w, 3 * k);
+    if (live && w == 0) fr_store(out + i, s);
 }
 
 // Gather one row across columns (open_batch) into a contiguous buffer.
@@ -392,18 +408,29 @@ extern "C" void lsp_mat_free(lsp_ctx* ctx, lsp_mat* m) {
 // ---------------------------------------------------------------------------
 namespace lsp {
 
+// One layer of 2-to-1 compressions.  Layers that cannot give every SM sub-partition a warp of
+// one-thread-per-node work are latency-bound: they take the three-lanes-per-node kernel.
+static int compress_layer(lsp_ctx* ctx, const Fr* in, Fr* out, size_t n_out) {
+    if (n_out <= size_t(ctx->sm_count) * 4 * 10) {
+        LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_compress_layer_tri<D>, unsigned((n_out + 9) / 10), 32, 0, ctx->p2, in, out, n_out));
+    } else {
+        LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
+                          LSP_LAUNCH(ctx, k_compress_layer<D>, grid_for(ctx, n_out, 128, 6), 128, 0, ctx->p2, in, out, n_out));
+    }
+    return LSP_OK;
+}
+
 // digests must hold 2h-1 elements; cols is a device array of `width` column pointers.
 int merkle_build(lsp_ctx* ctx, const Fr* const* d_cols, int width, size_t h, Fr* digests) {
     if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
     int log_h = ilog2(h);
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
-                      LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, h, 128), 128, 0, ctx->p2, d_cols, width, h, digests));
+                      LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, h, 128, 6), 128, 0, ctx->p2, d_cols, width, h, digests));
     for (int k = 0; k < log_h; k++) {
         size_t n_out = h >> (k + 1);
         const Fr* in = digests + tree_layer_offset(h, k);
         Fr* out = digests + tree_layer_offset(h, k + 1);
-        LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
-                          LSP_LAUNCH(ctx, k_compress_layer<D>, grid_for(ctx, n_out, 128), 128, 0, ctx->p2, in, out, n_out));
+        LSP_TRY(compress_layer(ctx, in, out, n_out));
     }
     return LSP_OK;
 }
@@ -419,8 +446,7 @@ int merkle_build_pairs(lsp_ctx* ctx, const Fr* vec, size_t len, Fr* digests) {
     for (int k = 0; k <= log_h; k++) {
         size_t n_out = h >> k;
         Fr* out = digests + tree_layer_offset(h, k);
-        LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
-                          LSP_LAUNCH(ctx, k_compress_layer<D>, grid_for(ctx, n_out, 128), 128, 0, ctx->p2, in, out, n_out));
+        LSP_TRY(compress_layer(ctx, in, out, n_out));
         in = out;
     }
     return LSP_OK;
@@ -520,7 +546,7 @@ extern "C" int lsp_hash_rows(lsp_ctx* ctx, const uint64_t* rowmajor, size_t rows
     LSP_TRY(dev_alloc(ctx, (void**)&dig, rows * 32));
     LSP_CUDA(ctx, cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(Fr*), cudaMemcpyHostToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, rows, 128), 128, 0, ctx->p2,
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, rows, 128, 6), 128, 0, ctx->p2,
                                                  (const Fr* const*)d_cols, int(width), rows, dig));
     LSP_CUDA(ctx, cudaMemcpyAsync(digests_out, dig, rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

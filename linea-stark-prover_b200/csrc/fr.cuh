@@ -193,19 +193,26 @@ __device__ __forceinline__ Fr fr_halve(const Fr& a) {
 // X + 2^32 Y += m * p, which clears X[0].  m comes out of an asm statement on purpose: when ptxas
 // sees m = -X[0] it rewrites m*p_i as X[0]*(-p_i) and then splits every one of these lanes into
 // IMAD + IMAD.HI.U32 (6 pipe cycles instead of 4).  p[0] = 1: that lane is an addition.
+// Pipe steering: ptxas implements m = -X[0] as IMAD.MOV (FMA-heavy pipe, 2 cycles there); the
+// form below (an add whose carry-out is consumed, then a NOT) stays on the ALU pipe.  The X and
+// Y carry chains are kept independent on purpose: writing the product as ONE unbroken chain
+// keeps every carry add on the ALU pipe too, but serialises ~180 instructions and was slower
+// (leaf hash 36.3 -> 38.2 ms, lone-warp permutation 43 -> 56 us).
 __device__ __forceinline__ void mont_reduce_step(uint32_t* X, uint32_t* Y) {
-    uint32_t m;
-    asm volatile("sub.u32 %0, 0, %1;" : "=r"(m) : "r"(X[0]));
+    uint32_t m, d;
     const uint32_t p1 = LSP_P1, p2 = LSP_P2, p3 = LSP_P3, p4 = LSP_P4, p5 = LSP_P5, p6 = LSP_P6, p7 = LSP_P7;
-    LSP_MADW_CC(Y[0], Y[1], p1, m);
-    LSP_MADWC_CC(Y[2], Y[3], p3, m);
-    LSP_MADWC_CC(Y[4], Y[5], p5, m);
-    LSP_MADWC_CC(Y[6], Y[7], p7, m);
-    asm volatile("add.cc.u32 %0, %0, %2;\n\taddc.cc.u32 %1, %1, 0;" : "+r"(X[0]), "+r"(X[1]) : "r"(m));
+    // d = X[0] - 1 carries exactly when X[0] != 0, which is the carry of X[0] + m*p[0] into X[1];
+    // m = -X[0] = ~(X[0] - 1).  (CC.CF is the adder's carry, also after sub.cc: not a borrow flag.)
+    asm volatile("add.cc.u32 %0, %2, 0xffffffff;\n\taddc.cc.u32 %1, %1, 0;" : "=r"(d), "+r"(X[1]) : "r"(X[0]));
+    asm volatile("not.b32 %0, %1;" : "=r"(m) : "r"(d));
     LSP_MADWC_CC(X[2], X[3], p2, m);
     LSP_MADWC_CC(X[4], X[5], p4, m);
     LSP_MADWC_CC(X[6], X[7], p6, m);
     LSP_ADDC0(Y[7]);
+    LSP_MADW_CC(Y[0], Y[1], p1, m);
+    LSP_MADWC_CC(Y[2], Y[3], p3, m);
+    LSP_MADWC_CC(Y[4], Y[5], p5, m);
+    asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(Y[6]), "+r"(Y[7]) : "r"(p7), "r"(m));
 }
 
 // Product half of a step on (X aligned at 2^0, Y aligned at 2^32): adds v * s where lane j of v
@@ -233,7 +240,7 @@ __device__ __forceinline__ void mont_row(uint32_t* X, uint32_t* Y, const uint32_
         if (5 >= FROM) LSP_MADWC3_CC(Y[4], Y[5], v[5], s, Z[6], Z[7]); else LSP_COPYC_CC(Y[4], Y[5], Z[6], Z[7]);
         asm volatile("madc.lo.cc.u32 %0, %2, %3, 0;\n\tmadc.hi.u32 %1, %2, %3, 0;" : "=r"(Y[6]), "=r"(Y[7]) : "r"(v[7]), "r"(s));
         if (0 >= FROM) LSP_MADW_CC(X[0], X[1], v[0], s);
-        if (2 >= FROM) { if (2 >= FROM && 0 < FROM) LSP_MADW_CC(X[2], X[3], v[2], s); else LSP_MADWC_CC(X[2], X[3], v[2], s); }
+        if (2 >= FROM) { if (0 < FROM) LSP_MADW_CC(X[2], X[3], v[2], s); else LSP_MADWC_CC(X[2], X[3], v[2], s); }
         if (4 >= FROM) { if (2 < FROM) LSP_MADW_CC(X[4], X[5], v[4], s); else LSP_MADWC_CC(X[4], X[5], v[4], s); }
         if (6 >= FROM) { if (4 < FROM) LSP_MADW_CC(X[6], X[7], v[6], s); else LSP_MADWC_CC(X[6], X[7], v[6], s); }
         if (6 >= FROM) LSP_ADDC0(Y[7]);
@@ -297,7 +304,7 @@ __device__ __forceinline__ Fr fr_sqr_lazy(const Fr& a) {
     sh[0] = db[0] = 0;
 #pragma unroll
     for (int j = 1; j < 8; j++) {
-        sh[j] = a.l[j] << 1;
+        asm("shf.l.clamp.b32 %0, 0, %1, 1;" : "=r"(sh[j]) : "r"(a.l[j]));  // a << 1 on the ALU pipe (ptxas would pick IMAD.IADD a+a)
         db[j] = __funnelshift_l(a.l[j - 1], a.l[j], 1);
     }
     uint32_t E[8], O[8], E2[8], O2[8];

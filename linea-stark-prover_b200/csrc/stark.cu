@@ -13,25 +13,28 @@ using namespace lsp;
 namespace lsp {
 
 // ===========================================================================
-// HashChallenger<Val,Hash,1> on the device.  All kernels run <<<1,1>>>: the
-// transcript is a serial chain by construction; keeping it on the device
-// removes every host round trip from prove().
+// HashChallenger<Val,Hash,1> on the device.  The transcript is a serial chain of
+// permutations by construction; keeping it on the device removes every host round
+// trip from prove().  The hashing kernels run as ONE WARP (<<<1,32>>>) on the
+// three-lanes-per-permutation shape (p2_permute_tri): a lone permutation costs 30
+// S-box latencies instead of 46.  Every lane triple computes the same digest.
 // ===========================================================================
 template <int D>
 __device__ __forceinline__ Fr ch_hash_input(const P2Params& P, const DevChallenger* ch) {
-    // PaddingFreeSponge<Perm,3,2,1>::hash_iter(input_buffer)
-    Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
-    int n = ch->n_input, i = 0;
-    for (; i + 1 < n; i += 2) {
-        s0 = ch->input[i];
-        s1 = ch->input[i + 1];
-        p2_permute<D>(P, s0, s1, s2);
+    // PaddingFreeSponge<Perm,3,2,1>::hash_iter(input_buffer); all 32 lanes call
+    const int lane = threadIdx.x & 31, k = lane / 3, w = lane - 3 * k;
+    Fr s = fr_zero();
+    const int n = ch->n_input;
+#pragma unroll 1
+    for (int i = 0; i < n; i += 2) {
+        if (w == 0) s = ch->input[i];
+        if (w == 1 && i + 1 < n) s = ch->input[i + 1];  // odd tail: state[1] keeps its stale value
+        p2_permute_tri<D>(P, s, w, 3 * k);
     }
-    if (i < n) {
-        s0 = ch->input[i];
-        p2_permute<D>(P, s0, s1, s2);
-    }
-    return s0;
+    Fr out;
+#pragma unroll
+    for (int i = 0; i < 8; i++) out.l[i] = __shfl_sync(0xffffffffu, s.l[i], 0);
+    return out;
 }
 
 // sample(): output_buffer is always empty when sample is called on this path
@@ -39,8 +42,12 @@ __device__ __forceinline__ Fr ch_hash_input(const P2Params& P, const DevChalleng
 template <int D>
 __device__ __forceinline__ Fr ch_sample(const P2Params& P, DevChallenger* ch) {
     Fr out = ch_hash_input<D>(P, ch);
-    ch->input[0] = out;
-    ch->n_input = 1;
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+        ch->input[0] = out;
+        ch->n_input = 1;
+    }
+    __syncwarp();
     return out;
 }
 
@@ -59,9 +66,9 @@ __global__ void k_ch_observe(DevChallenger* ch, const Fr* vals, int n) {
     for (int i = 0; i < n; i++) ch_observe(ch, fr_load(vals + i));
 }
 template <int D>
-__global__ void k_ch_sample(const __grid_constant__ P2Params P, DevChallenger* ch, Fr* out) {
+__global__ void __launch_bounds__(32) k_ch_sample(const __grid_constant__ P2Params P, DevChallenger* ch, Fr* out) {
     Fr v = ch_sample<D>(P, ch);
-    fr_store(out, v);
+    if (threadIdx.x == 0) fr_store(out, v);
 }
 // canonical integer of a Montgomery-form element: multiply by 1
 __device__ __forceinline__ Fr fr_from_mont(const Fr& a) {
@@ -70,10 +77,12 @@ __device__ __forceinline__ Fr fr_from_mont(const Fr& a) {
     return fr_mul(a, one);
 }
 template <int D>
-__global__ void k_ch_sample_bits(const __grid_constant__ P2Params P, DevChallenger* ch, int bits, int n, uint32_t* idx) {
+__global__ void __launch_bounds__(32) k_ch_sample_bits(const __grid_constant__ P2Params P, DevChallenger* ch, int bits, int n,
+                                                       uint32_t* idx) {
+#pragma unroll 1
     for (int q = 0; q < n; q++) {
         Fr c = fr_from_mont(ch_sample<D>(P, ch));
-        idx[q] = bits >= 32 ? c.l[0] : (c.l[0] & ((1u << bits) - 1u));
+        if (threadIdx.x == 0) idx[q] = bits >= 32 ? c.l[0] : (c.l[0] & ((1u << bits) - 1u));
     }
 }
 
@@ -81,43 +90,42 @@ __global__ void k_ch_sample_bits(const __grid_constant__ P2Params P, DevChalleng
 // challenger; the smallest passing witness of the first chunk that has one wins,
 // which makes the result deterministic (the reference's rayon find_any is not).
 template <int D>
-__global__ void __launch_bounds__(128) k_ch_grind_chunk(const __grid_constant__ P2Params P, const DevChallenger* ch, int bits,
-                                                        unsigned long long base, unsigned long long* best) {
+__global__ void __launch_bounds__(128, 4) k_ch_grind_chunk(const __grid_constant__ P2Params P, const DevChallenger* ch, int bits,
+                                                           unsigned long long base, unsigned long long* best) {
     unsigned long long w = base + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    // absorb everything before the final block of [input_buffer..., witness]
-    Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
-    int n = ch->n_input, i = 0;
-    for (; i + 1 < n; i += 2) {
-        s0 = ch->input[i];
-        s1 = ch->input[i + 1];
-        p2_permute<D>(P, s0, s1, s2);
-    }
     // witness as a field element: canonical w -> Montgomery
     Fr wf = fr_zero();
     wf.l[0] = uint32_t(w);
     wf.l[1] = uint32_t(w >> 32);
     wf = fr_mul(wf, fr_const(FR_R2));
-    if (i < n) {  // odd count: last block is [input[n-1], witness]
-        s0 = ch->input[i];
-        s1 = wf;
-    } else {      // even count: last block is [witness] alone, state[1] stale
-        s0 = wf;
+    // hash_iter([input_buffer..., witness]): odd count -> the last block is [input[n-1], witness];
+    // even count -> [witness] alone with state[1] stale
+    LSP_P2_SLOT_DECL(128);
+    Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
+    const int n = ch->n_input;
+#pragma unroll 1
+    for (int i = 0; i <= n; i += 2) {
+        s0 = i < n ? ch->input[i] : wf;
+        if (i + 1 <= n) s1 = i + 1 < n ? ch->input[i + 1] : wf;
+        p2_permute<D, 128>(P, s0, s1, s2, LSP_P2_SLOT(128));
     }
-    p2_permute<D>(P, s0, s1, s2);
     Fr c = fr_from_mont(s0);
     uint32_t low = bits >= 32 ? c.l[0] : (c.l[0] & ((1u << bits) - 1u));
     if (low == 0) atomicMin(best, w);
 }
 template <int D>
-__global__ void k_ch_apply_witness(const __grid_constant__ P2Params P, DevChallenger* ch, const unsigned long long* best,
-                                   Fr* witness_out) {
+__global__ void __launch_bounds__(32) k_ch_apply_witness(const __grid_constant__ P2Params P, DevChallenger* ch,
+                                                         const unsigned long long* best, Fr* witness_out) {
     unsigned long long w = *best;
     Fr wf = fr_zero();
     wf.l[0] = uint32_t(w);
     wf.l[1] = uint32_t(w >> 32);
     wf = fr_mul(wf, fr_const(FR_R2));
-    fr_store(witness_out, wf);
-    ch_observe(ch, wf);        // check_witness: observe(witness) ...
+    if (threadIdx.x == 0) {
+        fr_store(witness_out, wf);
+        ch_observe(ch, wf);    // check_witness: observe(witness) ...
+    }
+    __syncwarp();
     (void)ch_sample<D>(P, ch);  // ... then sample_bits(bits) consumes one sample
 }
 
@@ -130,11 +138,11 @@ int challenger_observe_dev(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals, int 
     return LSP_OK;
 }
 int challenger_sample(lsp_ctx* ctx, DevChallenger* ch, Fr* out_dev) {
-    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample<D>, 1, 1, 0, ctx->p2, ch, out_dev));
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample<D>, 1, 32, 0, ctx->p2, ch, out_dev));
     return LSP_OK;
 }
 int challenger_sample_bits(lsp_ctx* ctx, DevChallenger* ch, int bits, int n, uint32_t* idx_out) {
-    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample_bits<D>, 1, 1, 0, ctx->p2, ch, bits, n, idx_out));
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample_bits<D>, 1, 32, 0, ctx->p2, ch, bits, n, idx_out));
     return LSP_OK;
 }
 int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out) {
@@ -156,7 +164,7 @@ int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out)
             if (base > (1ull << 44)) return set_err(ctx, LSP_ERR_STATE, "grind: no witness found for %d bits", bits);
         }
     }
-    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_apply_witness<D>, 1, 1, 0, ctx->p2, ch, (const unsigned long long*)best, witness_out));
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_apply_witness<D>, 1, 32, 0, ctx->p2, ch, (const unsigned long long*)best, witness_out));
     dev_free(ctx, best);
     return LSP_OK;
 }
