@@ -217,21 +217,27 @@ extern "C" int lsp_kernel_timing_report(lsp_ctx* ctx, char* buf, size_t cap) {
     return LSP_OK;
 }
 
-// Integer-pipe peak of this device: independent IMAD.WIDE.U32 chains (the instruction the
-// Montgomery product is made of), timed with CUDA events.  Denominator of the integer roofline.
+// Integer-pipe peak of this device: eight independent IMAD.WIDE.U32 chains per thread with a
+// data-dependent multiplicand (the instruction the Montgomery product is made of; with
+// loop-invariant operands ptxas strength-reduces the multiply away and the "peak" doubles).
+// Timed with CUDA events.  Denominator of the integer roofline: 32x32->64 MACs per second.
 __global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, uint32_t seed, int iters) {
-    uint32_t a = threadIdx.x * 2654435761u + seed, b = blockIdx.x * 40503u + 17u + seed;
-    unsigned long long acc[8];
+    uint32_t b = blockIdx.x * 40503u + 17u + seed + threadIdx.x * 2654435761u;
+    uint32_t lo[8], hi[8];
 #pragma unroll
-    for (int c = 0; c < 8; c++) acc[c] = a + c;
+    for (int c = 0; c < 8; c++) {
+        lo[c] = (b + c) * 0x9e3779b9u;
+        hi[c] = (b ^ c) * 0x7f4a7c15u;
+    }
     for (int it = 0; it < iters; it++) {
 #pragma unroll
-        for (int c = 0; c < 8; c++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[c]) : "r"(a), "r"(b));
+        for (int c = 0; c < 8; c++)  // (lo,hi)[c] += lo[c+1] * b : one IMAD.WIDE.U32 with 64-bit accumulate
+            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[c]), "+r"(hi[c]) : "r"(lo[(c + 1) & 7]), "r"(b));
     }
-    unsigned long long r = 0;
+    uint32_t r = 0;
 #pragma unroll
-    for (int c = 0; c < 8; c++) r ^= acc[c];
-    out[blockIdx.x * blockDim.x + threadIdx.x] = uint32_t(r) ^ uint32_t(r >> 32);
+    for (int c = 0; c < 8; c++) r ^= lo[c] ^ hi[c];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 extern "C" int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s) {

@@ -1,0 +1,52 @@
+"""The CUDA library against the frozen fixtures of tests/golden/golden_v1.json, through the C ABI."""
+import pytest
+
+from oracle import poseidon2 as OP
+from tests.test_golden import GOLD, check_flat, instance, ix
+
+pytestmark = pytest.mark.gpu
+
+
+def test_field_vectors(gctx):
+    a = [ix(v["a"]) for v in GOLD["field"]]
+    b = [ix(v["b"]) for v in GOLD["field"]]
+    for op in ("add", "sub", "mul"):
+        assert gctx.fr_op(op, a, b) == [ix(v[op]) for v in GOLD["field"]]
+    assert gctx.fr_op("inv", a) == [ix(v["inv_a"]) for v in GOLD["field"]]
+    assert gctx.fr_op("halve", a) == [ix(v["halve_a"]) for v in GOLD["field"]]
+
+
+@pytest.mark.parametrize("entry", GOLD["poseidon2"], ids=lambda e: f"d{e['sbox_d']}")
+def test_poseidon2_vectors(pkg, entry):
+    p = OP.Poseidon2Params.from_seed(entry["seed"], sbox_d=entry["sbox_d"], rounds_f=entry["rounds_f"], rounds_p=entry["rounds_p"])
+    ctx = pkg.Context(0)
+    ctx.set_poseidon2(p.sbox_d, p.rounds_f, p.rounds_p, p.flat_constants(), p.internal_diag_m1)
+    assert ctx.permute([[ix(v) for v in c["in"]] for c in entry["cases"]]) == [[ix(v) for v in c["out"]] for c in entry["cases"]]
+    ctx.close()
+
+
+def test_sponge_lde_merkle_vectors(pkg, gctx):
+    assert gctx.hash_rows([[ix(v) for v in c["row"]] for c in GOLD["sponge"] if c["row"]]) == \
+        [ix(c["digest"]) for c in GOLD["sponge"] if c["row"]]
+    d = gctx.upload([[ix(v) for v in r] for r in GOLD["lde"]["in"]])
+    out = pkg.GpuDft(gctx).coset_lde_batch(d, GOLD["lde"]["added_bits"], ix(GOLD["lde"]["shift"]))
+    assert out.rows() == [[ix(v) for v in r] for r in GOLD["lde"]["out_bitrev_storage"]]
+    mm = pkg.GpuMmcs(gctx)
+    root, tree = mm.commit([out])
+    assert root == ix(GOLD["merkle"]["root"])
+    for k, layer in enumerate(GOLD["merkle"]["layers"]):
+        assert tree.layer(k) == [ix(v) for v in layer]
+    assert mm.open_batch(5, tree)[1] == [ix(v) for v in GOLD["merkle"]["open_5"]["siblings"]]
+    tree.free()
+    out.free()
+    d.free()
+
+
+@pytest.mark.parametrize("case", GOLD["proofs"], ids=lambda c: f"2^{c['log_n']}x{c['cols']}")
+def test_proof_vectors(pkg, gctx, case):
+    cfgs, trace, publics = instance(case)
+    g = [pkg.AirPermutationConfig(c.a_columns_ids, c.b_columns_ids, c.b_inverse_id, c.check_id) for c in cfgs]
+    proof = pkg.prove(gctx, pkg.FriConfig(**case["fri"]), g, trace, publics)
+    check_flat(case, proof.words)
+    gd, idx = proof.to_dict()
+    assert gd["commitments"]["trace"] == ix(case["trace_commit"]) and list(idx) == case["query_indices"]
