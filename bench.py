@@ -28,11 +28,15 @@ from pathlib import Path
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
+print_json = None   # set in main()
 sys.path.insert(0, str(ROOT))
 
 R_LIMBS = np.array([0x0a11800000000001, 0x59aa76fed0000001, 0x60b44d1e5c37b001, 0x12ab655e9a2ca556], dtype=np.uint64)
-MAC32_PER_MODMUL = 136          # CIOS on 8 x 32-bit limbs: 2*8^2 + 8
+MAC32_PER_MODMUL = 136          # CIOS on 8 x 32-bit limbs: 2*8^2 + 8, the algorithmic unit
 SBOX_MULS = {3: 2, 5: 3, 7: 4, 11: 5, 17: 5}
+# 32x32->64 products the kernels actually issue (one IMAD.WIDE each): product 64 + 56, square 36 + 56
+MUL_W, SQR_W = 120, 92
+SBOX_WIDE = {3: SQR_W + MUL_W, 5: 2 * SQR_W + MUL_W, 7: 2 * SQR_W + 2 * MUL_W, 11: 3 * SQR_W + 2 * MUL_W, 17: 4 * SQR_W + MUL_W}
 
 
 def random_fr_limbs(rng: np.random.Generator, n: int) -> np.ndarray:
@@ -180,14 +184,14 @@ def run_reference(args, rank, world):
     sample = (f"C port of the reference prover (oracle/c, OpenMP): full prove of a 2^{info['sample_log_n']}-row trace "
               f"took {info['sample_seconds']:.2f} s on {info['threads']} threads; scaled by Poseidon2 permutation "
               f"count x{info['scale']:.1f} to 2^{args.log_n} rows")
-    print(json.dumps({
+    print_json({
         "impl": "reference", "metric": "prove_seconds", "value": v, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "u256 (BLS12-377 Fr, Montgomery 4x64-bit)", "data": "synthetic",
         "config": workload_config(args, 1),
         "cpu_baseline": {"value": v, "unit": "s", "cores": info["threads"], "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def workload_config(args, world):
@@ -312,8 +316,15 @@ def run_gpu(args, rank, world, local_rank):
     achieved = leaf_bytes / (leaf_ms * 1e-3) / 1e9
     int_peak = ctx.int_peak()
     muls_per_perm = (8 * 3 + 22) * SBOX_MULS[args.sbox_d]
-    leaf_mac = big * ((w + 1) // 2) * muls_per_perm * MAC32_PER_MODMUL
+    wide_per_perm = (8 * 3 + 22) * SBOX_WIDE[args.sbox_d]
+    leaf_mac = big * ((w + 1) // 2) * wide_per_perm          # IMAD.WIDE the launch executes
     int_ach = leaf_mac / (leaf_ms * 1e-3)
+    traffic = None
+    tp_file = ROOT / "profiles" / "leaf_hash_dram_traffic.json"   # ncu --set full, dram__bytes_read+write of this launch
+    if tp_file.exists():
+        t = json.loads(tp_file.read_text())
+        if t["rows"] == big and t["width"] == w:
+            traffic = t["dram_bytes_per_launch"]
     tp, qp, fp = perm_counts(args.log_n, w, args.log_blowup, 2, 0)
     kern_total = sum(r["ms"] for r in kernel_report) / args.steps
     top = sorted(kernel_report, key=lambda r: -r["ms"])[:8]
@@ -329,13 +340,16 @@ def run_gpu(args, rank, world, local_rank):
         "lde_gb_per_s": (n + (n << args.log_blowup)) * w * 32 / (stage_acc.get("commit_trace_lde", float("nan")) * 1e-3) / 1e9,
         "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (trace LDE, %d rows x %d per launch)" % (big, w),
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                     "traffic": None, "peak_source": which, "ms_per_launch": leaf_ms,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": leaf_bytes, "peak_source": which, "ms_per_launch": leaf_ms,
                      "share_of_step": leaf["ms"] / args.steps / kern_total,
                      "note": "integer-pipe bound kernel: see int_roofline for the binding fraction"},
-        "int_roofline": {"bound": "int32 multiply pipe", "achieved": int_ach, "peak": int_peak, "unit": "MAC32/s",
-                         "frac": int_ach / int_peak, "mac32_per_modmul": MAC32_PER_MODMUL,
+        "int_roofline": {"bound": "int32 multiply (FMA-heavy) pipe", "achieved": int_ach, "peak": int_peak, "unit": "MAC32/s",
+                         "frac": int_ach / int_peak, "imad_wide_per_perm": wide_per_perm,
                          "modmuls_per_perm": muls_per_perm,
-                         "peak_source": "lsp_int_peak: independent IMAD.WIDE.U32 chains measured on this device"},
+                         "cios_mac32_per_s": big * ((w + 1) // 2) * muls_per_perm * MAC32_PER_MODMUL / (leaf_ms * 1e-3),
+                         "peak_source": "lsp_int_peak: independent data-dependent IMAD.WIDE.U32 chains timed on this device",
+                         "note": "achieved counts the 32x32->64 products the launch executes (120 per product, 92 per "
+                                 "square); cios_mac32_per_s is the same time against SURVEY's 136-MAC CIOS unit"},
         "top_kernels": [{"phase": r["phase"], "kernel": r["kernel"], "launches": r["launches"] // args.steps,
                          "ms": round(r["ms"] / args.steps, 3)} for r in top],
         "e2e": {"value": e2e_wall_ms / 1e3, "unit": "s", "h2d_bytes_per_step": n * w * 32 * world,
@@ -351,12 +365,19 @@ def run_gpu(args, rank, world, local_rank):
             "sample": (f"C port of the reference prover (oracle/c): full prove of a 2^{info['sample_log_n']}-row trace in "
                        f"{info['sample_seconds']:.2f} s on {info['threads']} threads ({info['perms_per_s']:.3g} Poseidon2 perms/s), "
                        f"scaled x{info['scale']:.1f} by permutation count to 2^{args.log_n} rows")}
-    print(json.dumps(out))
+    print_json(out)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL's version banner,
+    # torchrun notices) is sent to stderr, and the line is written to the saved descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_json
+    print_json = lambda obj: (real_stdout.write(json.dumps(obj) + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
