@@ -115,6 +115,21 @@ typedef struct {
     uint32_t check_id;
 } lsp_perm_air_cfg;
 
+/* ---- AIR config: `AirLookupConfig` (air/src/air_lookup.rs:2-11), the LogUp argument ---- */
+typedef struct {
+    uint32_t n_a_cols;              /* a_columns_ids.len()                                   */
+    const uint32_t* a_ids;          /* a_columns_ids                                         */
+    uint32_t n_tables;              /* b_columns_ids.len()                                   */
+    uint32_t n_b_cols;              /* b_columns_ids[t].len(), the same for every table      */
+    const uint32_t* b_ids;          /* b_columns_ids, table-major: n_tables x n_b_cols       */
+    uint32_t a_filter_id;
+    const uint32_t* b_filter_ids;   /* b_filter_id      [n_tables] */
+    uint32_t a_inverses_id;
+    const uint32_t* b_inverses_ids; /* b_inverses_id    [n_tables] */
+    const uint32_t* occurrences_ids;/* occurrences_id   [n_tables] */
+    uint32_t check_id;
+} lsp_lookup_air_cfg;
+
 /* `quotient_values` of p3-uni-stark with `LineaAIR::eval` -> `eval_permutation`
  * (air/src/lib.rs:47-54,116-167) folded by powers of `alpha`, times 1/Z_H.
  * `lde_bitrev` is the committed trace LDE; the first N<<log_q rows are read.
@@ -123,6 +138,16 @@ typedef struct {
 int lsp_quotient_permutation(lsp_ctx* ctx, const lsp_mat* lde_bitrev, int log_n, int log_q,
                              const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
                              const uint64_t alpha[4], lsp_mat** chunks_out);
+
+/* The same for a full `LineaAIR` (air/src/lib.rs:47-54): `eval_lookup` (:57-114) for every lookup
+ * config, then `eval_permutation` for every permutation config -- the order in which
+ * `RawTrace::push_traces` emits them (trace/src/lib.rs:80-89).  log_q = 2 when a lookup is
+ * present (its first-row constraint has degree 4), else 1. */
+int lsp_quotient_air(lsp_ctx* ctx, const lsp_mat* lde_bitrev, int log_n, int log_q,
+                     const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
+                     const uint64_t publics[2][4], const uint64_t alpha[4], lsp_mat** chunks_out);
+/* log2 of the number of quotient chunks `prove` uses for this AIR (`get_log_quotient_degree`). */
+int lsp_air_log_quotient_degree(int n_lookups, int n_perms);
 
 /* ---- FRI pieces of `TwoAdicFriPcs` (bin/src/config.rs:24-25) -------------- */
 /* `fold_matrix(beta, m)`: in = vector of 2h elements viewed as h rows of 2; out h elements. */
@@ -162,6 +187,16 @@ int lsp_prove_permutation(lsp_ctx* ctx, const lsp_fri_config* fri, const uint64_
 int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp_mat* trace,
                               const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
                               uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+
+/* `prove` for a `LineaAIR` holding lookup and permutation configs (what the reference's `main`
+ * proves at HEAD, bin/src/main.rs:37-43,76-86).  Proof layout as lsp_prove_permutation with
+ * q = 1 << lsp_air_log_quotient_degree(..) quotient chunks. */
+int lsp_prove_air(lsp_ctx* ctx, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
+                  const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
+                  const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+int lsp_prove_air_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp_mat* trace,
+                      const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
+                      const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
 
 /* ---- multi-GPU: one proof sharded by row ranges of the LDE ---------- */
 typedef struct lsp_comm lsp_comm;

@@ -261,6 +261,20 @@ class AirPermutationConfig:
         return len(self.a_columns_ids) + len(self.b_columns_ids) + 2
 
 
+class AirLookupConfig:
+    """`AirLookupConfig` (air/src/air_lookup.rs:2-39)."""
+
+    def __init__(self, a_columns_ids, b_columns_ids, a_filter_id, b_filter_id, a_inverses_id, b_inverses_id, occurrences_id, check_id):
+        self.a_columns_ids = list(a_columns_ids)
+        self.b_columns_ids = [list(t) for t in b_columns_ids]
+        self.a_filter_id, self.b_filter_id = int(a_filter_id), list(b_filter_id)
+        self.a_inverses_id, self.b_inverses_id = int(a_inverses_id), list(b_inverses_id)
+        self.occurrences_id, self.check_id = list(occurrences_id), int(check_id)
+
+    def width(self):
+        return len(self.a_columns_ids) + len(self.b_columns_ids) * (len(self.b_columns_ids[0]) + 3) + 3
+
+
 class FriConfig:
     """`FriConfig` literals of bin/src/main.rs:58-64."""
 
@@ -283,6 +297,33 @@ def _c_cfgs(cfgs):
         keep += [a, b]
         arr[i] = ffi.PermAirCfg(len(c.a_columns_ids), a, b, c.b_inverse_id, c.check_id)
     return arr, keep
+
+
+def _c_air_cfgs(cfgs):
+    """Splits a `LineaAIR` config list into the (lookups, permutations) arrays of the C ABI.  The reference
+    builds the list lookups-first (`RawTrace::push_traces`, trace/src/lib.rs:80-89) and the library folds the
+    constraints in that order, so any other interleaving is rejected."""
+    lookups = [c for c in cfgs if isinstance(c, AirLookupConfig)]
+    perms = [c for c in cfgs if not isinstance(c, AirLookupConfig)]
+    if list(cfgs) != lookups + perms:
+        raise BackendError("AIR configs must list lookups before permutations (RawTrace::push_traces order)")
+    keep = []
+    larr = (ffi.LookupAirCfg * max(1, len(lookups)))()
+    u32 = lambda xs: (C.c_uint32 * len(xs))(*xs)
+    for i, c in enumerate(lookups):
+        nb = len(c.b_columns_ids[0])
+        if any(len(t) != nb for t in c.b_columns_ids):
+            raise BackendError("every lookup table must have the same number of columns")
+        nt = len(c.b_columns_ids)
+        if not (len(c.b_filter_id) == len(c.b_inverses_id) == len(c.occurrences_id) == nt):
+            raise BackendError("lookup config: per-table id lists must have one entry per table")
+        bufs = [u32(c.a_columns_ids), u32([x for t in c.b_columns_ids for x in t]), u32(c.b_filter_id), u32(c.b_inverses_id),
+                u32(c.occurrences_id)]
+        keep += bufs
+        larr[i] = ffi.LookupAirCfg(len(c.a_columns_ids), bufs[0], nt, nb, bufs[1], c.a_filter_id, bufs[2], c.a_inverses_id, bufs[3],
+                                   bufs[4], c.check_id)
+    parr, pkeep = _c_cfgs(perms) if perms else ((ffi.PermAirCfg * 1)(), [])
+    return larr, len(lookups), parr, len(perms), keep + pkeep
 
 
 STAGE_NAMES = ["commit_trace_lde", "commit_trace_merkle", "quotient", "commit_quotient", "open_reduce",
@@ -346,7 +387,7 @@ def prove(ctx: Context, fri: FriConfig, cfgs, trace, publics, timings=None):
     `trace`: row-major list of rows (canonical ints), a uint64[n*w,4] limb array
     with `trace_shape=(n,w)` given via a tuple (array, n, w), or a device `Mat`."""
     cf = fri.c_struct()
-    arr, keep = _c_cfgs(cfgs)
+    larr, n_l, arr, n_p, keep = _c_air_cfgs(cfgs)
     pub = to_mont_array(publics)
     assert pub.shape == (2, 4)
     tm = np.zeros(8, dtype=np.float32)
@@ -361,18 +402,25 @@ def prove(ctx: Context, fri: FriConfig, cfgs, trace, publics, timings=None):
     if n & (n - 1) or n == 0:
         raise BackendError(f"trace height {n} is not a power of two")
     log_n = n.bit_length() - 1
-    log_q = 1
+    log_q = int(ctx.lib.lsp_air_log_quotient_degree(n_l, n_p))
     words = int(ctx.lib.lsp_proof_words(log_n, w, log_q, C.byref(cf)))
     if words == 0:
         raise BackendError("unsupported FRI parameters for this trace height")
     out = np.empty(words, dtype=np.uint64)
-    if isinstance(trace, Mat):
-        rc = ctx.lib.lsp_prove_permutation_dev(ctx.h, C.byref(cf), trace.h, arr, len(cfgs), ffi.as_u64p(pub),
-                                               ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    if n_l == 0:      # the permutation-only entry points (the benchmarked path)
+        if isinstance(trace, Mat):
+            rc = ctx.lib.lsp_prove_permutation_dev(ctx.h, C.byref(cf), trace.h, arr, n_p, ffi.as_u64p(pub),
+                                                   ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+        else:
+            rc = ctx.lib.lsp_prove_permutation(ctx.h, C.byref(cf), ffi.as_u64p(limbs), n, w, arr, n_p,
+                                               ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    elif isinstance(trace, Mat):
+        rc = ctx.lib.lsp_prove_air_dev(ctx.h, C.byref(cf), trace.h, larr, n_l, arr, n_p, ffi.as_u64p(pub),
+                                       ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
     else:
-        rc = ctx.lib.lsp_prove_permutation(ctx.h, C.byref(cf), ffi.as_u64p(limbs), n, w, arr, len(cfgs),
-                                           ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
-    ctx.check(rc, "lsp_prove_permutation")
+        rc = ctx.lib.lsp_prove_air(ctx.h, C.byref(cf), ffi.as_u64p(limbs), n, w, larr, n_l, arr, n_p,
+                                   ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    ctx.check(rc, "lsp_prove_air")
     if timings is not None:
         timings.update({k: float(v) for k, v in zip(STAGE_NAMES, tm)})
     del keep, width
@@ -387,6 +435,19 @@ def quotient_permutation(ctx: Context, lde: Mat, log_n: int, log_q: int, cfgs, p
     h = C.c_void_p()
     ctx.check(ctx.lib.lsp_quotient_permutation(ctx.h, lde.h, log_n, log_q, arr, len(cfgs), ffi.as_u64p(pub),
                                                ffi.as_u64p(al), C.byref(h)), "lsp_quotient_permutation")
+    del keep
+    return Mat(ctx, h)
+
+
+def quotient_air(ctx: Context, lde: Mat, log_n: int, cfgs, publics, alpha) -> Mat:
+    """`quotient_values` for a `LineaAIR` with lookup and permutation configs; N x q, q from the AIR's degree."""
+    larr, n_l, arr, n_p, keep = _c_air_cfgs(cfgs)
+    log_q = int(ctx.lib.lsp_air_log_quotient_degree(n_l, n_p))
+    pub = to_mont_array(publics)
+    al = to_mont_array([alpha])
+    h = C.c_void_p()
+    ctx.check(ctx.lib.lsp_quotient_air(ctx.h, lde.h, log_n, log_q, larr, n_l, arr, n_p, ffi.as_u64p(pub), ffi.as_u64p(al),
+                                       C.byref(h)), "lsp_quotient_air")
     del keep
     return Mat(ctx, h)
 

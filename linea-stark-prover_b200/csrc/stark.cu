@@ -172,10 +172,37 @@ int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out)
 // ===========================================================================
 // AIR config upload
 // ===========================================================================
-int upload_perm_cfgs(lsp_ctx* ctx, const lsp_perm_air_cfg* cfgs, int n_cfgs, size_t width, PermCfgDev* out, void** blob) {
-    if (!cfgs || n_cfgs <= 0) return set_err(ctx, LSP_ERR_PARAM, "no AIR configs");
+int upload_air_cfgs(lsp_ctx* ctx, const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* cfgs, int n_cfgs,
+                    size_t width, PermCfgDev* out, void** blob) {
+    if (n_lookups < 0 || n_cfgs < 0 || n_lookups + n_cfgs <= 0 || (n_lookups && !lookups) || (n_cfgs && !cfgs))
+        return set_err(ctx, LSP_ERR_PARAM, "no AIR configs");
     std::vector<uint32_t> h;
-    // layout: [n_cols x n][ids_off x n][b_inv x n][check x n][ids...]
+    size_t w_sum = 0;
+    // ---- lookups: [lk_off x n_lookups][records...]
+    std::vector<uint32_t> lk_off(n_lookups), lk;
+    auto in_range = [&](uint32_t id) { return size_t(id) < width; };
+    for (int i = 0; i < n_lookups; i++) {
+        const lsp_lookup_air_cfg& c = lookups[i];
+        if (c.n_a_cols == 0 || c.n_tables == 0 || c.n_b_cols == 0 || !c.a_ids || !c.b_ids || !c.b_filter_ids || !c.b_inverses_ids ||
+            !c.occurrences_ids)
+            return set_err(ctx, LSP_ERR_PARAM, "lookup config %d is incomplete", i);
+        bool ok = in_range(c.a_filter_id) && in_range(c.a_inverses_id) && in_range(c.check_id);
+        for (uint32_t k = 0; k < c.n_a_cols; k++) ok = ok && in_range(c.a_ids[k]);
+        for (uint32_t t = 0; t < c.n_tables; t++) {
+            ok = ok && in_range(c.b_filter_ids[t]) && in_range(c.b_inverses_ids[t]) && in_range(c.occurrences_ids[t]);
+            for (uint32_t k = 0; k < c.n_b_cols; k++) ok = ok && in_range(c.b_ids[size_t(t) * c.n_b_cols + k]);
+        }
+        if (!ok) return set_err(ctx, LSP_ERR_PARAM, "lookup config %d: column id out of range", i);
+        lk_off[i] = uint32_t(lk.size());
+        lk.insert(lk.end(), {c.n_a_cols, c.n_tables, c.n_b_cols, c.a_filter_id, c.a_inverses_id, c.check_id});
+        lk.insert(lk.end(), c.a_ids, c.a_ids + c.n_a_cols);
+        for (uint32_t t = 0; t < c.n_tables; t++) {
+            lk.insert(lk.end(), {c.b_filter_ids[t], c.b_inverses_ids[t], c.occurrences_ids[t]});
+            lk.insert(lk.end(), c.b_ids + size_t(t) * c.n_b_cols, c.b_ids + size_t(t + 1) * c.n_b_cols);
+        }
+        w_sum += size_t(c.n_a_cols) + size_t(c.n_tables) * (size_t(c.n_b_cols) + 3) + 3;  // air/src/air_lookup.rs:37-39
+    }
+    // ---- permutations: [n_cols x n][ids_off x n][b_inv x n][check x n][ids...]
     size_t total_ids = 0;
     for (int i = 0; i < n_cfgs; i++) {
         const lsp_perm_air_cfg& c = cfgs[i];
@@ -184,8 +211,11 @@ int upload_perm_cfgs(lsp_ctx* ctx, const lsp_perm_air_cfg* cfgs, int n_cfgs, siz
             if (c.a_ids[k] >= width || c.b_ids[k] >= width) return set_err(ctx, LSP_ERR_PARAM, "AIR config %d: column id out of range", i);
         if (c.b_inverse_id >= width || c.check_id >= width) return set_err(ctx, LSP_ERR_PARAM, "AIR config %d: column id out of range", i);
         total_ids += 2 * size_t(c.n_cols);
+        w_sum += 2 * size_t(c.n_cols) + 2;  // air/src/air_permutation.rs:21-23
     }
-    h.resize(4 * size_t(n_cfgs) + total_ids);
+    if (w_sum != width) return set_err(ctx, LSP_ERR_PARAM, "AIR width %zu != trace width %zu", w_sum, width);
+    const size_t perm_words = 4 * size_t(n_cfgs) + total_ids;
+    h.resize(perm_words + size_t(n_lookups) + lk.size());
     size_t off = 0;
     for (int i = 0; i < n_cfgs; i++) {
         h[i] = cfgs[i].n_cols;
@@ -196,6 +226,8 @@ int upload_perm_cfgs(lsp_ctx* ctx, const lsp_perm_air_cfg* cfgs, int n_cfgs, siz
         for (uint32_t k = 0; k < cfgs[i].n_cols; k++) h[4 * n_cfgs + off + cfgs[i].n_cols + k] = cfgs[i].b_ids[k];
         off += 2 * size_t(cfgs[i].n_cols);
     }
+    for (int i = 0; i < n_lookups; i++) h[perm_words + i] = lk_off[i];
+    for (size_t i = 0; i < lk.size(); i++) h[perm_words + n_lookups + i] = lk[i];
     uint32_t* d = nullptr;
     LSP_TRY(dev_alloc(ctx, (void**)&d, h.size() * 4));
     LSP_CUDA(ctx, cudaMemcpyAsync(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -206,8 +238,16 @@ int upload_perm_cfgs(lsp_ctx* ctx, const lsp_perm_air_cfg* cfgs, int n_cfgs, siz
     out->b_inverse_id = d + 2 * n_cfgs;
     out->check_id = d + 3 * n_cfgs;
     out->ids = d + 4 * n_cfgs;
+    out->n_lookups = n_lookups;
+    out->lk_off = d + perm_words;
+    out->lk = d + perm_words + n_lookups;
     *blob = d;
     return LSP_OK;
+}
+
+int upload_perm_cfgs(lsp_ctx* ctx, const lsp_perm_air_cfg* cfgs, int n_cfgs, size_t width, PermCfgDev* out, void** blob) {
+    if (!cfgs || n_cfgs <= 0) return set_err(ctx, LSP_ERR_PARAM, "no AIR configs");
+    return upload_air_cfgs(ctx, nullptr, 0, cfgs, n_cfgs, width, out, blob);
 }
 
 // ===========================================================================
@@ -389,6 +429,44 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
         Fr is_trans = fr_sub(x, w_n_inv);
         Fr acc = fr_zero();
         bool first_c = true;
+        // ---- eval_lookup (air/src/lib.rs:57-114), one pass per AirLookupConfig ----------------
+        for (int k = 0; k < A.cfg.n_lookups; k++) {
+            const uint32_t* r = A.cfg.lk + A.cfg.lk_off[k];
+            const uint32_t n_a = r[0], n_t = r[1], n_b = r[2];
+            const Fr* col_af = A.lde + size_t(r[3]) * A.lde_rows;
+            const Fr* col_ai = A.lde + size_t(r[4]) * A.lde_rows;
+            const Fr* col_chk = A.lde + size_t(r[5]) * A.lde_rows;
+            const uint32_t* a_ids = r + 6;
+            Fr a_l = fr_load_nc(A.lde + size_t(a_ids[0]) * A.lde_rows + p);        // :65-68
+            for (uint32_t j = 1; j < n_a; j++) a_l = fr_add(fr_mul(a_l, alpha_air), fr_load_nc(A.lde + size_t(a_ids[j]) * A.lde_rows + p));
+            a_l = fr_add(a_l, delta);                                               // :70
+            const Fr ai_l = fr_load_nc(col_ai + p), ai_n = fr_load_nc(col_ai + pn);
+            Fr c = fr_sub(fr_mul(a_l, ai_l), one);                                  // :73
+            acc = first_c ? c : fr_add(fr_mul(acc, alpha), c);
+            first_c = false;
+            Fr chk_l_expr = fr_mul(fr_load_nc(col_af + p), ai_l);                   // :75
+            Fr chk_n_expr = fr_mul(fr_load_nc(col_af + pn), ai_n);                  // :76
+            const uint32_t* t_rec = a_ids + n_a;
+            for (uint32_t t = 0; t < n_t; t++, t_rec += 3 + n_b) {
+                const Fr* col_bf = A.lde + size_t(t_rec[0]) * A.lde_rows;
+                const Fr* col_bi = A.lde + size_t(t_rec[1]) * A.lde_rows;
+                const Fr* col_oc = A.lde + size_t(t_rec[2]) * A.lde_rows;
+                const uint32_t* b_ids = t_rec + 3;
+                Fr b_l = fr_load_nc(A.lde + size_t(b_ids[0]) * A.lde_rows + p);     // :79-82
+                for (uint32_t j = 1; j < n_b; j++) b_l = fr_add(fr_mul(b_l, alpha_air), fr_load_nc(A.lde + size_t(b_ids[j]) * A.lde_rows + p));
+                b_l = fr_add(b_l, delta);                                           // :84
+                const Fr bi_l = fr_load_nc(col_bi + p), bi_n = fr_load_nc(col_bi + pn);
+                c = fr_sub(fr_mul(b_l, bi_l), one);                                 // :85-88
+                acc = fr_add(fr_mul(acc, alpha), c);
+                chk_l_expr = fr_sub(chk_l_expr, fr_mul(fr_mul(fr_load_nc(col_bf + p), fr_load_nc(col_oc + p)), bi_l));     // :90-92
+                chk_n_expr = fr_sub(chk_n_expr, fr_mul(fr_mul(fr_load_nc(col_bf + pn), fr_load_nc(col_oc + pn)), bi_n));   // :94-96
+            }
+            const Fr chk_l = fr_load_nc(col_chk + p), chk_n = fr_load_nc(col_chk + pn);
+            acc = fr_add(fr_mul(acc, alpha), fr_mul(is_first, fr_sub(chk_l, chk_l_expr)));                  // :100-102
+            acc = fr_add(fr_mul(acc, alpha), fr_mul(is_trans, fr_sub(fr_sub(chk_n, chk_l), chk_n_expr)));  // :105-107
+            acc = fr_add(fr_mul(acc, alpha), fr_mul(is_last, chk_l));                                       // :110-112
+        }
+        // ---- eval_permutation (air/src/lib.rs:116-167) -----------------------------------------
         for (int k = 0; k < A.cfg.n_cfgs; k++) {
             const uint32_t nc = A.cfg.n_cols[k];
             const uint32_t* a_ids = A.cfg.ids + A.cfg.ids_off[k];

@@ -53,7 +53,12 @@ struct DevChallenger {  // HashChallenger<Val,Hash,1> state, resident in device 
     int overflow;
 };
 
-struct PermCfgDev {  // flattened AirPermutationConfig list in device memory
+struct PermCfgDev {  // flattened LineaAIR config list in device memory: lookups first, then permutations
+    // lookup i lives at lk + lk_off[i]:
+    //   [n_a, n_tables, n_b, a_filter, a_inverses, check, a_ids[n_a], then per table: b_filter, b_inverses, occurrences, b_ids[n_b]]
+    int n_lookups = 0;
+    const uint32_t* lk_off = nullptr;
+    const uint32_t* lk = nullptr;
     int n_cfgs;
     const uint32_t* n_cols;    // per cfg
     const uint32_t* ids_off;   // per cfg, offset into ids (a ids then b ids)
@@ -72,6 +77,9 @@ int challenger_sample_bits(lsp_ctx* ctx, DevChallenger* ch, int bits, int n, uin
 int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out);
 
 int upload_perm_cfgs(lsp_ctx* ctx, const lsp_perm_air_cfg* cfgs, int n_cfgs, size_t width, PermCfgDev* out, void** blob);
+// lookups (may be empty) followed by permutations (may be empty); checks ids against `width` and that the widths add up to it
+int upload_air_cfgs(lsp_ctx* ctx, const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
+                    size_t width, PermCfgDev* out, void** blob);
 
 // E[p] = 1/(g*w_L^{bitrev(p)} - z) for p < 2^log_m, one array per point (points in device memory)
 int inverse_denominators(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m, Fr* const* out);

@@ -26,6 +26,14 @@ class PermAirCfg(C.Structure):
                 ("b_inverse_id", C.c_uint32), ("check_id", C.c_uint32)]
 
 
+class LookupAirCfg(C.Structure):
+    """`lsp_lookup_air_cfg` == reference `AirLookupConfig` (air/src/air_lookup.rs:2-11)."""
+    _fields_ = [("n_a_cols", C.c_uint32), ("a_ids", C.POINTER(C.c_uint32)), ("n_tables", C.c_uint32), ("n_b_cols", C.c_uint32),
+                ("b_ids", C.POINTER(C.c_uint32)), ("a_filter_id", C.c_uint32), ("b_filter_ids", C.POINTER(C.c_uint32)),
+                ("a_inverses_id", C.c_uint32), ("b_inverses_ids", C.POINTER(C.c_uint32)),
+                ("occurrences_ids", C.POINTER(C.c_uint32)), ("check_id", C.c_uint32)]
+
+
 class FriConfig(C.Structure):
     """`lsp_fri_config` == reference `FriConfig` literals (bin/src/main.rs:58-64)."""
     _fields_ = [("log_blowup", C.c_uint32), ("log_final_poly_len", C.c_uint32), ("num_queries", C.c_uint32),
@@ -73,6 +81,13 @@ SIGNATURES = {
     "lsp_comm_init_nccl": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(vp)]),
     "lsp_comm_init_local": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "lsp_comm_destroy": (None, [vp]),
+    "lsp_air_log_quotient_degree": (C.c_int, [C.c_int, C.c_int]),
+    "lsp_quotient_air": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(LookupAirCfg), C.c_int, C.POINTER(PermAirCfg), C.c_int,
+                                   u64p, u64p, C.POINTER(vp)]),
+    "lsp_prove_air": (C.c_int, [vp, C.POINTER(FriConfig), u64p, C.c_size_t, C.c_size_t, C.POINTER(LookupAirCfg), C.c_int,
+                                C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
+    "lsp_prove_air_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(LookupAirCfg), C.c_int, C.POINTER(PermAirCfg), C.c_int,
+                                    u64p, u64p, C.c_size_t, f32p]),
     "lsp_prove_permutation_sharded": (C.c_int, [vp, C.POINTER(FriConfig), u64p, C.c_size_t, C.c_size_t,
                                                 C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
     "lsp_prove_permutation_sharded_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(PermAirCfg), C.c_int, u64p, u64p,

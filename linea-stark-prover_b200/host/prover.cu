@@ -216,11 +216,12 @@ struct Scratch {  // frees everything it handed out when the prove call returns
     }
 };
 
-int max_constraint_log_quotient(const lsp_perm_air_cfg*, int) {
-    // `get_log_quotient_degree`: the permutation AIR's max constraint degree is 3
-    // (is_first_row * (check - a_ch * inv), air/src/lib.rs:146-148)
-    // => log2_ceil(3 - 1) = 1 whatever the column count.
-    return 1;
+int max_constraint_log_quotient(int n_lookups, int /*n_perms*/) {
+    // `get_log_quotient_degree`, log2_ceil(max degree - 1):
+    //   permutation AIR: max degree 3 (is_first_row * (check - a_ch * inv), air/src/lib.rs:146-148)      => 1
+    //   lookup AIR:      max degree 4 (is_first_row * (check - filter * inverse + ...), :100-102)        => 2
+    // whatever the column counts.
+    return n_lookups > 0 ? 2 : 1;
 }
 
 }  // namespace
@@ -237,15 +238,18 @@ extern "C" size_t lsp_proof_words(uint32_t log_n, uint32_t width, uint32_t log_q
     return elems * 4;
 }
 
-extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp_mat* trace,
-                                         const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
-                                         uint64_t* proof_out, size_t proof_words, float* timings_ms_out) {
-    if (!ctx || !fri || !trace || !cfgs || !publics || !proof_out) return LSP_ERR_PARAM;
+extern "C" int lsp_air_log_quotient_degree(int n_lookups, int n_perms) { return max_constraint_log_quotient(n_lookups, n_perms); }
+
+extern "C" int lsp_prove_air_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp_mat* trace, const lsp_lookup_air_cfg* lookups,
+                                 int n_lookups, const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                                 uint64_t* proof_out, size_t proof_words, float* timings_ms_out) {
+    if (!ctx || !fri || !trace || !publics || !proof_out || n_lookups < 0 || n_cfgs < 0 || n_lookups + n_cfgs <= 0) return LSP_ERR_PARAM;
+    if ((n_cfgs && !cfgs) || (n_lookups && !lookups)) return LSP_ERR_PARAM;
     if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
     const size_t n = trace->rows, W = trace->width;
     if (!is_pow2(n)) return set_err(ctx, LSP_ERR_PARAM, "trace height %zu is not a power of two (prove would panic)", n);
     const int log_n = ilog2(n);
-    const int log_q = max_constraint_log_quotient(cfgs, n_cfgs);
+    const int log_q = max_constraint_log_quotient(n_lookups, n_cfgs);
     const int q = 1 << log_q;
     const int log_b = int(fri->log_blowup), log_l = log_n + log_b;
     if (log_q > log_b) return set_err(ctx, LSP_ERR_PARAM, "quotient degree 2^%d exceeds blowup 2^%d", log_q, log_b);
@@ -254,9 +258,6 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     if (fri->num_queries == 0 || fri->num_queries > 4096) return set_err(ctx, LSP_ERR_PARAM, "num_queries out of range");
     const size_t need = lsp_proof_words(log_n, uint32_t(W), log_q, fri);
     if (proof_words < need) return set_err(ctx, LSP_ERR_PARAM, "proof buffer too small: %zu < %zu words", proof_words, need);
-    size_t w_sum = 0;
-    for (int i = 0; i < n_cfgs; i++) w_sum += 2 * size_t(cfgs[i].n_cols) + 2;
-    if (w_sum != W) return set_err(ctx, LSP_ERR_PARAM, "AIR width %zu != trace width %zu", w_sum, W);
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
 
     const size_t L = size_t(1) << log_l;
@@ -300,7 +301,7 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     Fr* p_queries = p_pow + 1;
     PermCfgDev cfg_dev;
     void* cfg_blob = nullptr;
-    LSP_TRY(upload_perm_cfgs(ctx, cfgs, n_cfgs, W, &cfg_dev, &cfg_blob));
+    LSP_TRY(upload_air_cfgs(ctx, lookups, n_lookups, cfgs, n_cfgs, W, &cfg_dev, &cfg_blob));  // also checks the AIR width
     S.ptrs.push_back(cfg_blob);
     mark();  // 0
 
@@ -455,15 +456,29 @@ extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri
     return LSP_OK;
 }
 
-extern "C" int lsp_prove_permutation(lsp_ctx* ctx, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
-                                     const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out,
-                                     size_t proof_words, float* timings_ms_out) {
+extern "C" int lsp_prove_air(lsp_ctx* ctx, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
+                             const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* cfgs, int n_cfgs,
+                             const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words, float* timings_ms_out) {
     if (!ctx || !trace) return LSP_ERR_PARAM;
     lsp_mat* m = nullptr;
     LSP_TRY(lsp_mat_upload(ctx, trace, rows, width, &m));
-    int rc = lsp_prove_permutation_dev(ctx, fri, m, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
+    int rc = lsp_prove_air_dev(ctx, fri, m, lookups, n_lookups, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
     lsp_mat_free(ctx, m);
     return rc;
+}
+
+extern "C" int lsp_prove_permutation_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp_mat* trace, const lsp_perm_air_cfg* cfgs,
+                                         int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words,
+                                         float* timings_ms_out) {
+    if (!cfgs || n_cfgs <= 0) return LSP_ERR_PARAM;
+    return lsp_prove_air_dev(ctx, fri, trace, nullptr, 0, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
+}
+
+extern "C" int lsp_prove_permutation(lsp_ctx* ctx, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
+                                     const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out,
+                                     size_t proof_words, float* timings_ms_out) {
+    if (!cfgs || n_cfgs <= 0) return LSP_ERR_PARAM;
+    return lsp_prove_air(ctx, fri, trace, rows, width, nullptr, 0, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
 }
 
 // ---------------------------------------------------------------------------
@@ -471,12 +486,19 @@ extern "C" int lsp_prove_permutation(lsp_ctx* ctx, const lsp_fri_config* fri, co
 // ---------------------------------------------------------------------------
 extern "C" int lsp_quotient_permutation(lsp_ctx* ctx, const lsp_mat* lde_bitrev, int log_n, int log_q, const lsp_perm_air_cfg* cfgs,
                                         int n_cfgs, const uint64_t publics[2][4], const uint64_t alpha[4], lsp_mat** chunks_out) {
-    if (!ctx || !lde_bitrev || !cfgs || !publics || !alpha || !chunks_out || log_n < 0 || log_q < 0 || log_n + log_q > 31) return LSP_ERR_PARAM;
+    if (!cfgs || n_cfgs <= 0) return LSP_ERR_PARAM;
+    return lsp_quotient_air(ctx, lde_bitrev, log_n, log_q, nullptr, 0, cfgs, n_cfgs, publics, alpha, chunks_out);
+}
+
+extern "C" int lsp_quotient_air(lsp_ctx* ctx, const lsp_mat* lde_bitrev, int log_n, int log_q, const lsp_lookup_air_cfg* lookups,
+                                int n_lookups, const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                                const uint64_t alpha[4], lsp_mat** chunks_out) {
+    if (!ctx || !lde_bitrev || !publics || !alpha || !chunks_out || log_n < 0 || log_q < 0 || log_n + log_q > 31) return LSP_ERR_PARAM;
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
     Scratch S(ctx);
     PermCfgDev cfg_dev;
     void* blob = nullptr;
-    LSP_TRY(upload_perm_cfgs(ctx, cfgs, n_cfgs, lde_bitrev->width, &cfg_dev, &blob));
+    LSP_TRY(upload_air_cfgs(ctx, lookups, n_lookups, cfgs, n_cfgs, lde_bitrev->width, &cfg_dev, &blob));
     S.ptrs.push_back(blob);
     Fr* sc = nullptr;
     LSP_TRY(S.get((void**)&sc, 3 * 32));

@@ -8,7 +8,7 @@ generator SURVEY.md 8(d) specifies.
 """
 from __future__ import annotations
 
-from .air import AirPermutationConfig
+from .air import AirLookupConfig, AirPermutationConfig
 from .field import R_MOD, SplitMix64, from_be_bytes_mod_order, inv
 
 
@@ -52,17 +52,96 @@ def permutation_columns(a, b, alpha: int, delta: int):
     return AirPermutationConfig.standard(width), cols
 
 
+def synthetic_lookup_input(seed: int, n_cols: int, n_tables: int, n: int, table_rows: int = 0, disabled_every: int = 0):
+    """A valid LogUp instance: (a, b, a_filter, b_filter) with a = n_cols columns of n looked-up rows,
+    b = n_tables tables of n_cols columns of n rows.  The `table_rows` distinct table rows (default
+    n//2, at least 1) are dealt round-robin over the tables, each table is padded with copies of its
+    own rows, and every A row is drawn from the table rows.  `disabled_every` > 0 switches the
+    filter off on every such A row and replaces that row by junk, which the argument must ignore."""
+    rng = SplitMix64(seed)
+    m = max(1, table_rows or n // 2)
+    m = min(m, n * n_tables)
+    rows = [[rng.next_fr() for _ in range(n_cols)] for _ in range(m)]
+    per_table = [[rows[i] for i in range(t, m, n_tables)] for t in range(n_tables)]
+    b = []
+    for t in range(n_tables):
+        src = per_table[t] or [rows[0]]
+        filled = [src[i % len(src)] for i in range(n)]
+        b.append([[filled[i][k] for i in range(n)] for k in range(n_cols)])
+    picks = [rows[rng.next_below(m)] for _ in range(n)]
+    a_filter = [1] * n
+    if disabled_every:
+        for i in range(0, n, disabled_every):
+            a_filter[i] = 0
+            picks[i] = [rng.next_fr() for _ in range(n_cols)]
+    a = [[picks[i][k] for i in range(n)] for k in range(n_cols)]
+    b_filter = [[1] * n for _ in range(n_tables)]
+    return a, b, a_filter, b_filter
+
+
+def lookup_columns(a, b, a_filter, b_filter, alpha: int, delta: int):
+    """`RawLookupTrace::get_trace` (`trace/src/lookup.rs:46-176`): columns a.., b (table by table).., a_filter,
+    b_filters, 1/(a_comb+delta), per-table 1/(b_comb+delta), per-table multiplicities, running log-derivative sum."""
+    sz = len(a[0])
+    comb = lambda cols, i: _horner(cols, i, alpha)
+    occurrences = {}
+    for i in range(sz):                                   # :83-104
+        if a_filter[i] == 0:
+            continue
+        k = comb(a, i)
+        occurrences[k] = occurrences.get(k, 0) + 1
+    a_inv_col, b_inv_tab, mult_tab, prefix = [], [[] for _ in b], [[] for _ in b], []
+    total = 0
+    for i in range(sz):                                   # :120-163
+        ai = inv((comb(a, i) + delta) % R_MOD)
+        a_inv_col.append(ai)
+        if a_filter[i] != 0:
+            total = (total + ai) % R_MOD
+        for t, table in enumerate(b):
+            bc = comb(table, i)
+            bi = inv((bc + delta) % R_MOD)
+            b_inv_tab[t].append(bi)
+            occ = 0
+            if bc in occurrences and b_filter[t][i] != 0:
+                occ = occurrences.pop(bc)
+                total = (total - bi * occ) % R_MOD
+            mult_tab[t].append(occ)
+        prefix.append(total)
+    if prefix[-1] != 0:                                   # :165-168
+        raise AssertionError("failed to check constrain: check column should be 0 on the last row")
+    cols = [list(x) for x in a]
+    for table in b:
+        cols += [list(x) for x in table]
+    cols += [list(a_filter)] + [list(f) for f in b_filter] + [a_inv_col] + b_inv_tab + mult_tab + [prefix]
+    return AirLookupConfig.standard(len(a), len(b), len(b[0])), cols
+
+
+def _horner(cols, i, alpha):
+    acc = 0
+    for col in cols:
+        acc = (acc * alpha + col[i]) % R_MOD
+    return acc
+
+
 def row_major(cols):
     """`RawTrace::get_trace` (`trace/src/lib.rs:94-106`)."""
     h = len(cols[0])
     return [[cols[c][r] for c in range(len(cols))] for r in range(h)]
 
 
-def build_trace(perm_inputs, alpha: int, delta: int):
-    """`RawTrace::push_traces` for permutation traces only (`trace/src/lib.rs:62-92`):
-    pads every input to the tallest, concatenates columns, shifts configs."""
-    height = max(max(len(col) for col in a + b) for a, b in perm_inputs)
+def build_trace(perm_inputs, alpha: int, delta: int, lookup_inputs=()):
+    """`RawTrace::push_traces` (`trace/src/lib.rs:62-92`): lookup traces first, then permutation traces;
+    pads every permutation input to the tallest, concatenates columns, shifts configs.  (Lookup inputs
+    must already have the common height: zero-padding a lookup changes its multiplicities.)"""
+    heights = [max(len(col) for col in a + b) for a, b in perm_inputs] + [len(l[0][0]) for l in lookup_inputs]
+    height = max(heights)
     cols, cfgs = [], []
+    for a, b, af, bf in lookup_inputs:
+        assert len(a[0]) == height
+        cfg, lc = lookup_columns(a, b, af, bf, alpha, delta)
+        cfg.shift(len(cols))
+        cols += lc
+        cfgs.append(cfg)
     for a, b in perm_inputs:
         a = [col + [0] * (height - len(col)) for col in a]   # `resize`, permutation.rs:134-142
         b = [col + [0] * (height - len(col)) for col in b]

@@ -1,0 +1,103 @@
+"""LogUp lookup AIR: `LineaAIR::eval_lookup` (air/src/lib.rs:57-114) in the fused
+quotient kernel and the full prove with q = 4 quotient chunks, against the oracle.  This is the AIR the
+reference's `main` proves at HEAD (bin/src/main.rs:37-43).  Bit-exact."""
+import copy
+
+import pytest
+
+from oracle import air as OA
+from oracle import dft as OD
+from oracle import field as F
+from oracle import stark as OS
+from oracle import trace as OT
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_cfgs(pkg, cfgs):
+    out = []
+    for c in cfgs:
+        if isinstance(c, OA.AirLookupConfig):
+            out.append(pkg.AirLookupConfig(c.a_columns_ids, c.b_columns_ids, c.a_filter_id, c.b_filter_id, c.a_inverses_id,
+                                           c.b_inverses_id, c.occurrences_id, c.check_id))
+        else:
+            out.append(pkg.AirPermutationConfig(c.a_columns_ids, c.b_columns_ids, c.b_inverse_id, c.check_id))
+    return out
+
+
+def _instance(log_n, lookups, perms, seed):
+    """lookups: list of (n_cols, n_tables, disabled_every); perms: list of column counts."""
+    n = 1 << log_n
+    rng = F.SplitMix64(seed)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    lk = [OT.synthetic_lookup_input(seed + 3 * i, nc, nt, n, disabled_every=de) for i, (nc, nt, de) in enumerate(lookups)]
+    pm = [OT.synthetic_permutation_input(seed + 100 + i, c, n) for i, c in enumerate(perms)]
+    cfgs, trace = OT.build_trace(pm, alpha, delta, lk)
+    assert OA.check_constraints(cfgs, trace, [alpha, delta])
+    return cfgs, trace, [alpha, delta]
+
+
+def test_lookup_witness_layout_matches_reference_ids():
+    """Column ids of `get_air_lookup_config` (trace/src/lookup.rs:178-214) and `AirLookupConfig::width`."""
+    c = OA.AirLookupConfig.standard(2, 3, 2)
+    assert c.a_columns_ids == [0, 1] and c.b_columns_ids == [[2, 3], [4, 5], [6, 7]]
+    assert (c.a_filter_id, c.b_filter_id, c.a_inverses_id) == (8, [9, 10, 11], 12)
+    assert (c.b_inverses_id, c.occurrences_id, c.check_id) == ([13, 14, 15], [16, 17, 18], 19)
+    assert c.width() == 20 == 2 + 3 * (2 + 3) + 3
+
+
+@pytest.mark.parametrize("log_n,lookups,perms", [
+    (2, [(1, 1, 0)], []),
+    (4, [(2, 2, 5)], []),
+    (5, [(3, 1, 0), (1, 3, 7)], [2]),
+    (7, [(2, 1, 3)], [3, 1]),
+])
+def test_quotient_values_with_lookups(pkg, gctx, log_n, lookups, perms):
+    cfgs, trace, publics = _instance(log_n, lookups, perms, 900 + log_n)
+    log_q = OA.log_quotient_degree(cfgs)
+    assert log_q == 2
+    lde = OD.coset_lde_batch(trace, 3, F.GENERATOR)
+    td, qd = OS.Domain(log_n, 1), OS.Domain(log_n + log_q, F.GENERATOR)
+    alpha = F.SplitMix64(77).next_fr()
+    qv = OS.quotient_values(cfgs, publics, td, qd, OD.bit_reverse_rows(lde[:qd.size()]), alpha)
+    got = pkg.quotient_air(gctx, gctx.upload(lde), log_n, _gpu_cfgs(pkg, cfgs), publics, alpha).rows()
+    assert got == [[qv[k * 4 + ch] for ch in range(4)] for k in range(1 << log_n)]
+
+
+@pytest.mark.parametrize("log_n,lookups,perms,fri", [
+    (3, [(1, 1, 0)], [], dict(log_blowup=2, log_final_poly_len=0, num_queries=5, proof_of_work_bits=0)),
+    (5, [(2, 2, 6)], [2], dict(log_blowup=3, log_final_poly_len=0, num_queries=33, proof_of_work_bits=0)),
+    (6, [(3, 1, 0), (2, 2, 9)], [], dict(log_blowup=3, log_final_poly_len=1, num_queries=7, proof_of_work_bits=3)),
+])
+def test_prove_lookup_air_bit_exact_and_verifies(pkg, gctx, p2params, log_n, lookups, perms, fri):
+    cfgs, trace, publics = _instance(log_n, lookups, perms, 40 + log_n)
+    ofri = OS.FriConfig(**fri)
+    dbg = {}
+    oproof = OS.prove(p2params, ofri, cfgs, trace, publics, dbg)
+    OS.verify(p2params, ofri, cfgs, oproof, publics)
+    gproof = pkg.prove(gctx, pkg.FriConfig(**fri), _gpu_cfgs(pkg, cfgs), trace, publics)
+    assert gproof.log_q == 2
+    gd, indices = gproof.to_dict()
+    assert len(gd["opened_values"]["quotient_chunks"]) == 4
+    assert gd == oproof and indices == dbg["query_indices"]
+    OS.verify(p2params, ofri, cfgs, gd, publics)
+    bad = copy.deepcopy(gd)
+    qc = bad["opened_values"]["quotient_chunks"]
+    if isinstance(qc[3], list):
+        qc[3][0] = (qc[3][0] + 1) % F.R_MOD
+    else:
+        qc[3] = (qc[3] + 1) % F.R_MOD
+    with pytest.raises(OS.VerificationError):
+        OS.verify(p2params, ofri, cfgs, bad, publics)
+
+
+def test_lookup_air_needs_blowup_4(pkg, gctx):
+    cfgs, trace, publics = _instance(3, [(1, 1, 0)], [], 5)
+    with pytest.raises(pkg.BackendError, match="quotient degree"):
+        pkg.prove(gctx, pkg.FriConfig(log_blowup=1), _gpu_cfgs(pkg, cfgs), trace, publics)
+
+
+def test_lookup_configs_must_come_first(pkg, gctx):
+    cfgs, trace, publics = _instance(3, [(1, 1, 0)], [1], 6)
+    with pytest.raises(pkg.BackendError, match="lookups before permutations"):
+        pkg.prove(gctx, pkg.FriConfig(), list(reversed(_gpu_cfgs(pkg, cfgs))), trace, publics)
