@@ -162,6 +162,17 @@ int lsp_fri_fold(lsp_ctx* ctx, const lsp_mat* in, const uint64_t beta[4], lsp_ma
 int lsp_permutation_trace(lsp_ctx* ctx, const uint64_t* ab_rowmajor, size_t rows, uint32_t n_cols,
                           const uint64_t publics[2][4], lsp_mat** trace_out);
 
+/* ---- input wire format: `RawPermutationTrace` as CBOR (trace/src/permutation.rs:9-22) ---------- */
+/* `read_file` (:17-22): pure parsing, no GPU.  `_shape` reports the height (tallest column) and the
+ * number of a (= b) columns; `_decode` writes every element's 32 big-endian bytes row-major,
+ * rows x 2*n_cols (a columns first), zero-padding short columns (`resize`, :134-142). */
+int lsp_cbor_permutation_shape(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_cols, char* name, size_t name_cap);
+int lsp_cbor_permutation_decode(const uint8_t* cbor, size_t len, uint8_t* be_rowmajor, size_t rows, uint32_t n_cols);
+/* `get_columns` (`from_be_bytes_mod_order`, :95-118) + `get_trace` (:24-93) on the device: like
+ * lsp_permutation_trace, from raw 32-byte big-endian values (any value < 2^256, reduced mod r). */
+int lsp_permutation_trace_be(lsp_ctx* ctx, const uint8_t* be_rowmajor, size_t rows, uint32_t n_cols,
+                             const uint64_t publics[2][4], lsp_mat** trace_out);
+
 /* ---- `prove` (bin/src/main.rs:80-86) ------------------------------------- */
 typedef struct {
     uint32_t log_blowup;          /* FriConfig.log_blowup        (main.rs:59) */

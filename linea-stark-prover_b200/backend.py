@@ -98,6 +98,15 @@ class Context:
         return Mat(self, h)
 
     # -- Perm::new_from_rng constants handed over (bin/src/main.rs:49) --------
+    def permutation_trace_be(self, be_bytes: np.ndarray, n: int, c: int, publics_limbs: np.ndarray) -> "Mat":
+        """`get_columns` + `get_trace` from raw 32-byte big-endian values (uint8[n*2c*32], row-major, a columns first)."""
+        be = np.ascontiguousarray(be_bytes, dtype=np.uint8)
+        assert be.size == n * 2 * c * 32
+        h = C.c_void_p()
+        self.check(self.lib.lsp_permutation_trace_be(self.h, be.ctypes.data, n, c, ffi.as_u64p(publics_limbs), C.byref(h)),
+                   "lsp_permutation_trace_be")
+        return Mat(self, h)
+
     def set_poseidon2(self, sbox_d, rounds_f, rounds_p, flat_constants, diag_m1=(1, 1, 2)):
         c = to_mont_array(flat_constants)
         d = to_mont_array(diag_m1)
@@ -297,6 +306,20 @@ def _c_cfgs(cfgs):
         keep += [a, b]
         arr[i] = ffi.PermAirCfg(len(c.a_columns_ids), a, b, c.b_inverse_id, c.check_id)
     return arr, keep
+
+
+def read_raw_permutation_trace(blob: bytes):
+    """`RawPermutationTrace::read_file` (trace/src/permutation.rs:17-22) through the library's CBOR parser
+    (host-only entry points: no GPU needed).  Returns (be_bytes uint8[rows*2c*32], rows, n_cols, name)."""
+    lib = ffi.load()
+    rows, nc = C.c_size_t(), C.c_uint32()
+    name = C.create_string_buffer(256)
+    if lib.lsp_cbor_permutation_shape(blob, len(blob), C.byref(rows), C.byref(nc), name, 256) != 0:
+        raise BackendError("not a CBOR RawPermutationTrace")
+    out = np.zeros(rows.value * 2 * nc.value * 32, dtype=np.uint8)
+    if lib.lsp_cbor_permutation_decode(blob, len(blob), out.ctypes.data, rows.value, nc.value) != 0:
+        raise BackendError("malformed CBOR RawPermutationTrace")
+    return out, rows.value, nc.value, name.value.decode()
 
 
 def _c_air_cfgs(cfgs):

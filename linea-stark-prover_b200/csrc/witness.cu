@@ -152,8 +152,35 @@ __global__ void k_check_last_is_one(const Fr* __restrict__ v, size_t n, int* __r
 
 }  // namespace
 
+// `from_be_bytes_mod_order` + Montgomery conversion, in place: 32 big-endian bytes -> x*R mod r.
+// x < 2^256 goes in as the unrestricted operand of the lazy product with R^2 (< r).
+__global__ void __launch_bounds__(128) k_be_to_mont(Fr* __restrict__ v, size_t count) {
+    const Fr r2 = fr_const(FR_R2);
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) {
+        Fr be = fr_load(v + i), x;
+#pragma unroll
+        for (int k = 0; k < 8; k++) x.l[k] = __byte_perm(be.l[7 - k], 0, 0x0123);
+        Fr y = fr_mul_lazy(r2, x);
+        fr_reduce_once(y);
+        fr_store(v + i, y);
+    }
+}
+
+static int permutation_trace_impl(lsp_ctx* ctx, const void* ab_rowmajor, bool big_endian_bytes, size_t rows, uint32_t n_cols,
+                                  const uint64_t publics[2][4], lsp_mat** trace_out);
+
 extern "C" int lsp_permutation_trace(lsp_ctx* ctx, const uint64_t* ab_rowmajor, size_t rows, uint32_t n_cols,
                                      const uint64_t publics[2][4], lsp_mat** trace_out) {
+    return permutation_trace_impl(ctx, ab_rowmajor, false, rows, n_cols, publics, trace_out);
+}
+
+extern "C" int lsp_permutation_trace_be(lsp_ctx* ctx, const uint8_t* be_rowmajor, size_t rows, uint32_t n_cols,
+                                        const uint64_t publics[2][4], lsp_mat** trace_out) {
+    return permutation_trace_impl(ctx, be_rowmajor, true, rows, n_cols, publics, trace_out);
+}
+
+static int permutation_trace_impl(lsp_ctx* ctx, const void* ab_rowmajor, bool big_endian_bytes, size_t rows, uint32_t n_cols,
+                                  const uint64_t publics[2][4], lsp_mat** trace_out) {
     if (!ctx || !ab_rowmajor || !publics || !trace_out || rows == 0 || n_cols == 0) return LSP_ERR_PARAM;
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t n = rows, w_in = 2 * size_t(n_cols), w_out = w_in + 2;
@@ -168,6 +195,7 @@ extern "C" int lsp_permutation_trace(lsp_ctx* ctx, const uint64_t* ab_rowmajor, 
     LSP_TRY(mat_alloc(ctx, n, w_out, &m));
     LSP_CUDA(ctx, cudaMemcpyAsync(stage, ab_rowmajor, n * w_in * 32, cudaMemcpyHostToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaMemcpyAsync(pub, publics, 64, cudaMemcpyHostToDevice, ctx->stream));
+    if (big_endian_bytes) LSP_LAUNCH(ctx, k_be_to_mont, grid_for(ctx, n * w_in, 128), 128, 0, stage, n * w_in);
     Fr* den = m->d + w_in * n;
     Fr* num = den + n;
     LSP_LAUNCH(ctx, k_wit_combine, grid_for(ctx, n, 128), 128, 0, (const Fr*)stage, n, int(n_cols), (const Fr*)pub, m->d);
