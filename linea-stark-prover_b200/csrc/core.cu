@@ -52,13 +52,18 @@ __global__ void __launch_bounds__(128) k_p2_permute(const __grid_constant__ P2Pa
     }
 }
 
+// Resident 128-thread blocks per SM the one-thread-per-permutation kernels are compiled for (64 registers, no spills, at 8; measured 4..8: 102.5, 102.0, 100.4, 100.0, 98.7 ms per prove).
+#ifndef LSP_P2_MINB
+#define LSP_P2_MINB 8
+#endif
+
 // Leaf digests: one thread per row.  PaddingFreeSponge<Perm,3,2,1>::hash_iter over
 // the concatenation of that row in every matrix (overwrite mode, rate 2).
 // cols[] are column base pointers (column-major storage => coalesced across rows).
 // The permutation is inlined at ONE site (odd tail folded into the loop): the kernel stays
 // inside the instruction cache.
 template <int D>
-__global__ void __launch_bounds__(128, 6) k_leaf_hash(const __grid_constant__ P2Params P, const Fr* const* __restrict__ cols,
+__global__ void __launch_bounds__(128, LSP_P2_MINB) k_leaf_hash(const __grid_constant__ P2Params P, const Fr* const* __restrict__ cols,
                                                    int width, size_t rows, Fr* __restrict__ digests) {
     LSP_P2_SLOT_DECL(128);
     for (size_t r = blockIdx.x * size_t(blockDim.x) + threadIdx.x; r < rows; r += size_t(gridDim.x) * blockDim.x) {
@@ -75,7 +80,7 @@ __global__ void __launch_bounds__(128, 6) k_leaf_hash(const __grid_constant__ P2
 
 // One Merkle layer: out[i] = compress(in[2i], in[2i+1]).
 template <int D>
-__global__ void __launch_bounds__(128, 6) k_compress_layer(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
+__global__ void __launch_bounds__(128, LSP_P2_MINB) k_compress_layer(const __grid_constant__ P2Params P, const Fr* __restrict__ in,
                                                         Fr* __restrict__ out, size_t n_out) {
     LSP_P2_SLOT_DECL(128);
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n_out; i += size_t(gridDim.x) * blockDim.x) {
@@ -421,7 +426,7 @@ static int compress_layer(lsp_ctx* ctx, const Fr* in, Fr* out, size_t n_out) {
         LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_compress_layer_tri<D>, unsigned((n_out + 9) / 10), 32, 0, ctx->p2, in, out, n_out));
     } else {
         LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
-                          LSP_LAUNCH(ctx, k_compress_layer<D>, grid_for(ctx, n_out, 128, 6), 128, 0, ctx->p2, in, out, n_out));
+                          LSP_LAUNCH(ctx, k_compress_layer<D>, grid_for(ctx, n_out, 128, LSP_P2_MINB), 128, 0, ctx->p2, in, out, n_out));
     }
     return LSP_OK;
 }
@@ -431,7 +436,7 @@ int merkle_build(lsp_ctx* ctx, const Fr* const* d_cols, int width, size_t h, Fr*
     if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
     int log_h = ilog2(h);
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d,
-                      LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, h, 128, 6), 128, 0, ctx->p2, d_cols, width, h, digests));
+                      LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, h, 128, LSP_P2_MINB), 128, 0, ctx->p2, d_cols, width, h, digests));
     for (int k = 0; k < log_h; k++) {
         size_t n_out = h >> (k + 1);
         const Fr* in = digests + tree_layer_offset(h, k);
@@ -552,7 +557,7 @@ extern "C" int lsp_hash_rows(lsp_ctx* ctx, const uint64_t* rowmajor, size_t rows
     LSP_TRY(dev_alloc(ctx, (void**)&dig, rows * 32));
     LSP_CUDA(ctx, cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(Fr*), cudaMemcpyHostToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, rows, 128, 6), 128, 0, ctx->p2,
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, rows, 128, LSP_P2_MINB), 128, 0, ctx->p2,
                                                  (const Fr* const*)d_cols, int(width), rows, dig));
     LSP_CUDA(ctx, cudaMemcpyAsync(digests_out, dig, rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -13,7 +13,8 @@ from pathlib import Path
 import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = PKG_DIR / "liblsp_b200.so"
+# LSP_B200_LIB selects another build of the same library (tuning experiments); the default is the in-tree one
+LIB_PATH = Path(os.environ.get("LSP_B200_LIB") or PKG_DIR / "liblsp_b200.so")
 
 u64p = C.POINTER(C.c_uint64)
 f32p = C.POINTER(C.c_float)
