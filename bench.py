@@ -144,6 +144,7 @@ def cpu_sample_prove(log_n_full: int, c: int, fri_kw: dict, sbox_d: int, budget_
     from oracle import air as OA
     from oracle import stark as OS
     from oracle.poseidon2 import Poseidon2Params
+    cport.set_threads(0)   # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1)
     cport.set_poseidon2(Poseidon2Params.from_seed(0xB200, sbox_d=sbox_d))
     fri = OS.FriConfig(**fri_kw)
     cfgs = [OA.AirPermutationConfig.standard(c)]

@@ -647,6 +647,18 @@ int lsp_oracle_gen_trace(uint64_t seed, uint32_t c, uint32_t log_n, uint64_t* pu
     return fr_eq(prev, ONE) ? 0 : -2;                 /* permutation.rs:76-79 */
 }
 
+/* n <= 0: one thread per online processor, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1). */
+int lsp_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n <= 0) n = omp_get_num_procs();
+    omp_set_num_threads(n);
+    return n;
+#else
+    (void)n;
+    return 1;
+#endif
+}
+
 int lsp_oracle_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -138,3 +138,8 @@ def gen_trace(seed: int, c: int, log_n: int):
 
 def threads() -> int:
     return int(load().lsp_oracle_threads())
+
+
+def set_threads(n: int = 0) -> int:
+    """n <= 0: every online processor, overriding OMP_NUM_THREADS (torchrun exports OMP_NUM_THREADS=1)."""
+    return int(load().lsp_oracle_set_threads(int(n)))
