@@ -322,6 +322,21 @@ def read_raw_permutation_trace(blob: bytes):
     return out, rows.value, nc.value, name.value.decode()
 
 
+def read_raw_lookup_trace(blob: bytes):
+    """`RawLookupTrace::read_file` (trace/src/lookup.rs:20-44) through the library's CBOR parser (host only).
+    Returns (be_bytes uint8[rows*(n_a + T*n_b + 1 + T)*32], rows, n_a, n_tables, n_b, name)."""
+    lib = ffi.load()
+    rows, na, nt, nb = C.c_size_t(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    name = C.create_string_buffer(256)
+    if lib.lsp_cbor_lookup_shape(blob, len(blob), C.byref(rows), C.byref(na), C.byref(nt), C.byref(nb), name, 256) != 0:
+        raise BackendError("not a CBOR RawLookupTrace")
+    stride = na.value + nt.value * nb.value + 1 + nt.value
+    out = np.zeros(rows.value * stride * 32, dtype=np.uint8)
+    if lib.lsp_cbor_lookup_decode(blob, len(blob), out.ctypes.data, rows.value, na.value, nt.value, nb.value) != 0:
+        raise BackendError("malformed CBOR RawLookupTrace")
+    return out, rows.value, na.value, nt.value, nb.value, name.value.decode()
+
+
 def _c_air_cfgs(cfgs):
     """Splits a `LineaAIR` config list into the (lookups, permutations) arrays of the C ABI.  The reference
     builds the list lookups-first (`RawTrace::push_traces`, trace/src/lib.rs:80-89) and the library folds the

@@ -165,3 +165,33 @@ def decode_raw_permutation_trace(blob: bytes):
     obj = cbor2.loads(blob)
     dec = lambda cols: [[from_be_bytes_mod_order(bytes(x)) for x in col] for col in cols]
     return dec(obj["a"]), dec(obj["b"]), obj["name"]
+
+
+def encode_raw_lookup_trace(a, b, a_filter, b_filter, name: str) -> bytes:
+    """CBOR of `RawLookupTrace` (`trace/src/lookup.rs:10-17`); filters may be shorter than the columns or absent
+    (`[]`): `read_file` fills them in."""
+    import cbor2
+    e = lambda x: list(int(x).to_bytes(32, "big"))
+    return cbor2.dumps({"a": [[e(x) for x in col] for col in a], "b": [[[e(x) for x in col] for col in t] for t in b], "name": name,
+                        "a_filter": [e(x) for x in a_filter], "b_filter": [[e(x) for x in f] for f in b_filter]})
+
+
+def decode_raw_lookup_trace(blob: bytes, height: int | None = None):
+    """`read_file` (`trace/src/lookup.rs:20-44`: default filters), `resize` to `height` (default: the trace's own
+    max height, :215-246) and `get_columns` (:248-301).  Returns (a, b, a_filter, b_filter, name), canonical ints."""
+    import cbor2
+    obj = cbor2.loads(blob)
+    d = lambda x: from_be_bytes_mod_order(bytes(x))
+    a = [[d(x) for x in col] for col in obj["a"]]
+    b = [[[d(x) for x in col] for col in t] for t in obj["b"]]
+    af = [d(x) for x in obj.get("a_filter", [])]
+    bf = [[d(x) for x in f] for f in obj.get("b_filter", [])]
+    af += [1] * (len(a[0]) - len(af))                      # :29-31
+    bf += [[] for _ in range(len(b) - len(bf))]            # :33-35
+    for t in range(len(b)):                                # :37-41
+        bf[t] += [1] * (len(b[t][0]) - len(bf[t]))
+    h = height if height is not None else max([len(c) for c in a] + [len(c) for t in b for c in t])
+    pad = lambda v: (v + [0] * (h - len(v)))[:h]
+    a = [pad(c) for c in a]
+    b = [[pad(c) for c in t] for t in b]
+    return a, b, pad(af), [pad(f) for f in bf[:len(b)]], obj["name"]

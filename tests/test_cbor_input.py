@@ -99,3 +99,50 @@ def test_cbor_file_to_proof(pkg, gctx, p2params):
     gd, _ = pkg.prove(gctx, pkg.FriConfig(**fri), g, dev, [alpha, delta]).to_dict()
     assert gd == OS.prove(p2params, OS.FriConfig(**fri), cfgs, trace, [alpha, delta])
     assert OA.check_constraints(cfgs, trace, [alpha, delta])
+
+
+def _be_lookup(a, b, af, bf, rows):
+    cols = list(a) + [c for t in b for c in t] + [af] + list(bf)
+    out = np.zeros((rows, len(cols), 32), dtype=np.uint8)
+    for j, col in enumerate(cols):
+        for i, x in enumerate(col):
+            out[i, j] = np.frombuffer(int(x).to_bytes(32, "big"), dtype=np.uint8)
+    return out.reshape(-1)
+
+
+def test_lookup_decode_matches_oracle(pkg):
+    a, b, af, bf = OT.synthetic_lookup_input(21, 2, 3, 16, disabled_every=4)
+    blob = OT.encode_raw_lookup_trace(a, b, af, bf, "lookup_0")
+    be, rows, na, nt, nb, name = pkg.read_raw_lookup_trace(blob)
+    assert (rows, na, nt, nb, name) == (16, 2, 3, 2, "lookup_0")
+    da, db, daf, dbf, _ = OT.decode_raw_lookup_trace(blob)
+    assert (da, db, daf, dbf) == (a, b, af, bf)
+    assert np.array_equal(be, _be_lookup(a, b, af, bf, 16))
+
+
+def test_lookup_default_filters_and_padding(pkg):
+    """`read_file` fills absent filters with ones up to the guarded column's length (trace/src/lookup.rs:25-41);
+    `resize` then pads columns AND filters with zeros (:230-246)."""
+    a = [[5, 6, 7], [1, 2, 3]]                       # 3 rows
+    b = [[[5, 6, 7, 9, 9], [1, 2, 3, 9, 9]],         # table 0: 5 rows  -> trace height 5
+         [[5, 5], [1, 1]]]                           # table 1: 2 rows
+    blob = OT.encode_raw_lookup_trace(a, b, [0], [[1, 0]], "d")   # a_filter has 1 entry, b_filter only for table 0
+    be, rows, na, nt, nb, _ = pkg.read_raw_lookup_trace(blob)
+    assert (rows, na, nt, nb) == (5, 2, 2, 2)
+    da, db, daf, dbf, _ = OT.decode_raw_lookup_trace(blob)
+    assert daf == [0, 1, 1, 0, 0]                    # given, ones up to len(a[0]) = 3, zero padding
+    assert dbf == [[1, 0, 1, 1, 1], [1, 1, 0, 0, 0]]
+    assert np.array_equal(be, _be_lookup(da, db, daf, dbf, 5))
+
+
+def test_lookup_malformed_is_rejected(pkg):
+    a, b, af, bf = OT.synthetic_lookup_input(22, 1, 2, 4)
+    obj = cbor2.loads(OT.encode_raw_lookup_trace(a, b, af, bf, "x"))
+    obj["b"][1] = obj["b"][1] + obj["b"][1]          # tables of different widths
+    with pytest.raises(pkg.BackendError):
+        pkg.read_raw_lookup_trace(cbor2.dumps(obj))
+    del obj["b"]
+    with pytest.raises(pkg.BackendError):
+        pkg.read_raw_lookup_trace(cbor2.dumps(obj))
+    with pytest.raises(pkg.BackendError):
+        pkg.read_raw_lookup_trace(OT.encode_raw_lookup_trace(a, b, af, bf, "x")[:100])
