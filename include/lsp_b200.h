@@ -181,6 +181,18 @@ int lsp_cbor_lookup_decode(const uint8_t* cbor, size_t len, uint8_t* be_rowmajor
 int lsp_permutation_trace_be(lsp_ctx* ctx, const uint8_t* be_rowmajor, size_t rows, uint32_t n_cols,
                              const uint64_t publics[2][4], lsp_mat** trace_out);
 
+/* `RawLookupTrace::get_trace` (trace/src/lookup.rs:46-176) on the device: from the decoded input
+ * (row layout as lsp_cbor_lookup_decode: a.., b.., a_filter, b_filter[T]) and publics = [alpha, delta],
+ * builds the rows x (n_a + T*(n_b+3) + 3) lookup trace -- inverses, multiplicities (the count of every
+ * enabled A row goes to the first enabled B row holding the same combination) and the running
+ * log-derivative sum.  Fails (LSP_ERR_PARAM) when the sum does not end at 0 (the assert of :165-168). */
+int lsp_lookup_trace(lsp_ctx* ctx, const uint64_t* in_rowmajor, size_t rows, uint32_t n_a_cols, uint32_t n_tables,
+                     uint32_t n_b_cols, const uint64_t publics[2][4], lsp_mat** trace_out);
+int lsp_lookup_trace_be(lsp_ctx* ctx, const uint8_t* be_rowmajor, size_t rows, uint32_t n_a_cols, uint32_t n_tables,
+                        uint32_t n_b_cols, const uint64_t publics[2][4], lsp_mat** trace_out);
+/* `RawTrace::push_traces` (trace/src/lib.rs:62-92): sub-traces of one height side by side, in the order given. */
+int lsp_mat_hconcat(lsp_ctx* ctx, const lsp_mat* const* mats, int n_mats, lsp_mat** out);
+
 /* ---- `prove` (bin/src/main.rs:80-86) ------------------------------------- */
 typedef struct {
     uint32_t log_blowup;          /* FriConfig.log_blowup        (main.rs:59) */

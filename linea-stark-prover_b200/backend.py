@@ -107,6 +107,25 @@ class Context:
                    "lsp_permutation_trace_be")
         return Mat(self, h)
 
+    def lookup_trace(self, data, n: int, n_a: int, n_tables: int, n_b: int, publics_limbs: np.ndarray) -> "Mat":
+        """`RawLookupTrace::get_trace` on the device.  `data`: uint64[n*w_in,4] Montgomery limbs, or uint8 raw
+        big-endian bytes (n*w_in*32), rows of  a.., b (table by table).., a_filter, b_filter[T]."""
+        h = C.c_void_p()
+        if data.dtype == np.uint8:
+            d = np.ascontiguousarray(data)
+            rc = self.lib.lsp_lookup_trace_be(self.h, d.ctypes.data, n, n_a, n_tables, n_b, ffi.as_u64p(publics_limbs), C.byref(h))
+        else:
+            rc = self.lib.lsp_lookup_trace(self.h, ffi.as_u64p(data), n, n_a, n_tables, n_b, ffi.as_u64p(publics_limbs), C.byref(h))
+        self.check(rc, "lsp_lookup_trace")
+        return Mat(self, h)
+
+    def hconcat(self, mats) -> "Mat":
+        """`RawTrace::push_traces` column concatenation."""
+        arr = (C.c_void_p * len(mats))(*[m.h for m in mats])
+        h = C.c_void_p()
+        self.check(self.lib.lsp_mat_hconcat(self.h, arr, len(mats), C.byref(h)), "lsp_mat_hconcat")
+        return Mat(self, h)
+
     def set_poseidon2(self, sbox_d, rounds_f, rounds_p, flat_constants, diag_m1=(1, 1, 2)):
         c = to_mont_array(flat_constants)
         d = to_mont_array(diag_m1)

@@ -82,9 +82,9 @@ def test_cbor_file_to_proof(pkg, gctx, p2params):
     alpha, delta = rng.next_fr(), rng.next_fr()
     a, b = OT.synthetic_permutation_input(8, c, n)
     # a few non-canonical encodings of the same row in a and b: `from_be_bytes_mod_order` reduces them
+    k = next(i for i in range(n) if all(b[t][i] == a[t][3] for t in range(c)))
     for j in range(c):
         v = a[j][3]
-        k = next(i for i in range(n) if all(b[t][i] == a[t][3] for t in range(c)))
         a[j][3] = v + F.R_MOD
         b[j][k] = v + 2 * F.R_MOD
     blob = OT.encode_raw_permutation_trace(a, b, "mxp")

@@ -101,3 +101,68 @@ def test_lookup_configs_must_come_first(pkg, gctx):
     cfgs, trace, publics = _instance(3, [(1, 1, 0)], [1], 6)
     with pytest.raises(pkg.BackendError, match="lookups before permutations"):
         pkg.prove(gctx, pkg.FriConfig(), list(reversed(_gpu_cfgs(pkg, cfgs))), trace, publics)
+
+
+def _lookup_rows(a, b, af, bf):
+    n = len(a[0])
+    cols = list(a) + [c for t in b for c in t] + [af] + list(bf)
+    return [x for i in range(n) for x in (col[i] for col in cols)]
+
+
+@pytest.mark.parametrize("log_n,n_cols,n_tables,disabled", [(0, 1, 1, 0), (3, 1, 1, 0), (5, 2, 3, 4), (9, 3, 2, 7), (12, 1, 2, 0)])
+def test_lookup_witness_on_device(pkg, gctx, log_n, n_cols, n_tables, disabled):
+    """lsp_lookup_trace == RawLookupTrace::get_trace (trace/src/lookup.rs:46-176), column for column."""
+    n = 1 << log_n
+    rng = F.SplitMix64(300 + log_n)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    a, b, af, bf = OT.synthetic_lookup_input(50 + log_n, n_cols, n_tables, n, disabled_every=disabled)
+    if n >= 8:
+        # the same row in two tables, and a DISABLED earlier holder: the count must go to the first ENABLED holder
+        for k in range(n_cols):
+            b[-1][k][1] = b[0][k][2]
+        bf[0][0] = 0
+    cfg, cols = OT.lookup_columns(a, b, af, bf, alpha, delta)
+    pub = pkg.to_mont_array([alpha, delta])
+    got = gctx.lookup_trace(pkg.to_mont_array(_lookup_rows(a, b, af, bf)), n, n_cols, n_tables, n_cols, pub)
+    assert got.width == cfg.width()
+    assert got.rows() == OT.row_major(cols)
+
+
+def test_lookup_witness_rejects_missing_value(pkg, gctx):
+    rng = F.SplitMix64(9)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    a, b, af, bf = OT.synthetic_lookup_input(60, 2, 1, 16)
+    a[0][3] = 424242
+    pub = pkg.to_mont_array([alpha, delta])
+    with pytest.raises(pkg.BackendError, match="check column should be 0"):
+        gctx.lookup_trace(pkg.to_mont_array(_lookup_rows(a, b, af, bf)), 16, 2, 1, 2, pub)
+    af[3] = 0   # the filter switches the offending row off
+    gctx.lookup_trace(pkg.to_mont_array(_lookup_rows(a, b, af, bf)), 16, 2, 1, 2, pub)
+
+
+def test_main_flow_cbor_files_to_proof(pkg, gctx, p2params):
+    """What the reference's `main` does at HEAD (bin/src/main.rs:35-86): read a lookup file (and here a
+    permutation file too), `push_traces` (lookups first), `LineaAIR::new(cfgs)`, `prove` -- all on the device
+    from the CBOR bytes; trace and proof equal the oracle's."""
+    n = 32
+    rng = F.SplitMix64(12)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    lk = OT.synthetic_lookup_input(70, 2, 2, n)
+    # filters partly omitted in the file -> `read_file` defaults them to one: a_filter = [0, 1, 1, 1, ...]
+    lk_blob = OT.encode_raw_lookup_trace(lk[0], lk[1], [0, 1, 1], [lk[3][0]], "lookup_0")
+    pa, pb = OT.synthetic_permutation_input(71, 3, n)
+    pm_blob = OT.encode_raw_permutation_trace(pa, pb, "perm_0")
+    pub = pkg.to_mont_array([alpha, delta])
+    be, rows, na, nt, nb, _ = pkg.read_raw_lookup_trace(lk_blob)
+    t_lk = gctx.lookup_trace(be, rows, na, nt, nb, pub)
+    be, rows, nc, _ = pkg.read_raw_permutation_trace(pm_blob)
+    t_pm = gctx.permutation_trace_be(be, rows, nc, pub)
+    trace_dev = gctx.hconcat([t_lk, t_pm])
+    dl = OT.decode_raw_lookup_trace(lk_blob)
+    cfgs, trace = OT.build_trace([(pa, pb)], alpha, delta, [dl[:4]])
+    assert trace_dev.rows() == trace
+    fri = dict(log_blowup=3, log_final_poly_len=0, num_queries=6, proof_of_work_bits=0)
+    gd, _ = pkg.prove(gctx, pkg.FriConfig(**fri), _gpu_cfgs(pkg, cfgs), trace_dev, [alpha, delta]).to_dict()
+    oproof = OS.prove(p2params, OS.FriConfig(**fri), cfgs, trace, [alpha, delta])
+    assert gd == oproof
+    OS.verify(p2params, OS.FriConfig(**fri), cfgs, gd, [alpha, delta])
