@@ -8,6 +8,7 @@ import pytest
 from oracle import air as OA
 from oracle import dft as OD
 from oracle import field as F
+from oracle import poseidon2 as OP
 from oracle import stark as OS
 from oracle import trace as OT
 
@@ -212,4 +213,27 @@ def test_baseline_configs_verify(pkg, name, log_n, c, log_blowup):
     bad = gproof.words.copy()
     bad[4 * 3 + 1] ^= 1 << 7
     assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, bad) != 0
+    ctx.close()
+
+
+@pytest.mark.parametrize("d,rf,rp,diag", [(3, 8, 22, (1, 1, 2)), (7, 8, 22, (1, 1, 2)), (11, 8, 22, (1, 1, 2)), (17, 8, 22, (1, 1, 2)),
+                                          (5, 6, 13, (3, 5, 7)), (17, 4, 0, (1, 1, 2))])
+def test_prove_with_other_poseidon2_parameters(pkg, d, rf, rp, diag):
+    """Nothing fork-specific is baked in: S-box degree, round counts and the internal
+    diagonal are run-time parameters of both permutation shapes (one thread / three lanes per permutation),
+    so whole proofs must stay bit-identical to the oracle's for every supported choice."""
+    from oracle.poseidon2 import Poseidon2Params
+    p = Poseidon2Params.from_seed(1000 + d, sbox_d=d, rounds_f=rf, rounds_p=rp)
+    p.internal_diag_m1 = diag
+    ctx = pkg.Context(0)
+    ctx.set_poseidon2(d, rf, rp, p.flat_constants(), diag)
+    cfgs, trace, publics = _perm_instance(5, 2, 60 + d)
+    fri = dict(log_blowup=2, log_final_poly_len=0, num_queries=6, proof_of_work_bits=3)
+    gd, _ = pkg.prove(ctx, pkg.FriConfig(**fri), _gpu_cfgs(pkg, cfgs), trace, publics).to_dict()
+    assert gd == OS.prove(p, OS.FriConfig(**fri), cfgs, trace, publics)
+    OS.verify(p, OS.FriConfig(**fri), cfgs, gd, publics)
+    # both permutation shapes on the same states: thread-per-permutation probe vs the tree the tri-lane kernel built
+    rng = F.SplitMix64(d)
+    states = [[rng.next_fr(), rng.next_fr(), 0] for _ in range(64)]
+    assert [s[0] for s in ctx.permute(states)] == [OP.compress(p, s[0], s[1]) for s in states]
     ctx.close()
