@@ -249,6 +249,14 @@ int lsp_prove_permutation_sharded_dev(lsp_comm* comm, const lsp_fri_config* fri,
                                       const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
                                       uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
 
+/* The same for a `LineaAIR` with lookup configs (4 quotient chunks; needs log_blowup >= 2). */
+int lsp_prove_air_sharded(lsp_comm* comm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
+                          const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
+                          const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+int lsp_prove_air_sharded_dev(lsp_comm* comm, const lsp_fri_config* fri, const lsp_mat* trace,
+                              const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
+                              const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -571,7 +571,7 @@ def prove_sharded(comm: Comm, fri: FriConfig, cfgs, trace, publics, timings=None
     """`prove` with the LDE / Merkle / FRI work sharded over comm's ranks.  Same proof as `prove`."""
     ctx = comm.ctx
     cf = fri.c_struct()
-    arr, keep = _c_cfgs(cfgs)
+    larr, n_l, arr, n_p, keep = _c_air_cfgs(cfgs)
     pub = to_mont_array(publics)
     tm = np.zeros(8, dtype=np.float32)
     if isinstance(trace, Mat):
@@ -584,18 +584,19 @@ def prove_sharded(comm: Comm, fri: FriConfig, cfgs, trace, publics, timings=None
     if n & (n - 1) or n == 0:
         raise BackendError(f"trace height {n} is not a power of two")
     log_n = n.bit_length() - 1
-    words = int(ctx.lib.lsp_proof_words(log_n, w, 1, C.byref(cf)))
+    log_q = int(ctx.lib.lsp_air_log_quotient_degree(n_l, n_p))
+    words = int(ctx.lib.lsp_proof_words(log_n, w, log_q, C.byref(cf)))
     if words == 0:
         raise BackendError("unsupported FRI parameters for this trace height")
     out = np.empty(words, dtype=np.uint64)
     if isinstance(trace, Mat):
-        rc = ctx.lib.lsp_prove_permutation_sharded_dev(comm.h, C.byref(cf), trace.h, arr, len(cfgs), ffi.as_u64p(pub),
-                                                       ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+        rc = ctx.lib.lsp_prove_air_sharded_dev(comm.h, C.byref(cf), trace.h, larr, n_l, arr, n_p, ffi.as_u64p(pub),
+                                               ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
     else:
-        rc = ctx.lib.lsp_prove_permutation_sharded(comm.h, C.byref(cf), ffi.as_u64p(limbs), n, w, arr, len(cfgs),
-                                                   ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
-    ctx.check(rc, "lsp_prove_permutation_sharded")
+        rc = ctx.lib.lsp_prove_air_sharded(comm.h, C.byref(cf), ffi.as_u64p(limbs), n, w, larr, n_l, arr, n_p,
+                                           ffi.as_u64p(pub), ffi.as_u64p(out), words, tm.ctypes.data_as(ffi.f32p))
+    ctx.check(rc, "lsp_prove_air_sharded")
     if timings is not None:
         timings.update({k: float(v) for k, v in zip(STAGE_NAMES, tm)})
     del keep
-    return Proof(out, log_n, w, 1, fri)
+    return Proof(out, log_n, w, log_q, fri)

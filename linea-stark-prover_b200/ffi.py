@@ -82,6 +82,10 @@ SIGNATURES = {
     "lsp_comm_init_nccl": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(vp)]),
     "lsp_comm_init_local": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),
     "lsp_comm_destroy": (None, [vp]),
+    "lsp_prove_air_sharded": (C.c_int, [vp, C.POINTER(FriConfig), u64p, C.c_size_t, C.c_size_t, C.POINTER(LookupAirCfg), C.c_int,
+                                        C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
+    "lsp_prove_air_sharded_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(LookupAirCfg), C.c_int, C.POINTER(PermAirCfg),
+                                            C.c_int, u64p, u64p, C.c_size_t, f32p]),
     "lsp_air_log_quotient_degree": (C.c_int, [C.c_int, C.c_int]),
     "lsp_cbor_permutation_shape": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t]),
     "lsp_cbor_permutation_decode": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32]),

@@ -413,16 +413,17 @@ extern "C" void lsp_comm_destroy(lsp_comm* cm) {
     delete cm;
 }
 
-extern "C" int lsp_prove_permutation_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri, const lsp_mat* tr, const lsp_perm_air_cfg* cfgs,
-                                                 int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words,
-                                                 float* timings_ms_out) {
-    if (!cm || !fri || !tr || !cfgs || !publics || !proof_out) return LSP_ERR_PARAM;
+extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri, const lsp_mat* tr, const lsp_lookup_air_cfg* lookups,
+                                         int n_lookups, const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                                         uint64_t* proof_out, size_t proof_words, float* timings_ms_out) {
+    if (!cm || !fri || !tr || !publics || !proof_out || n_lookups < 0 || n_cfgs < 0 || n_lookups + n_cfgs <= 0) return LSP_ERR_PARAM;
+    if ((n_cfgs && !cfgs) || (n_lookups && !lookups)) return LSP_ERR_PARAM;
     lsp_ctx* ctx = cm->ctx;
     if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
     const size_t n = tr->rows, W = tr->width;
     if (!is_pow2(n)) return set_err(ctx, LSP_ERR_PARAM, "trace height %zu is not a power of two (prove would panic)", n);
     const int G = cm->world, log_g = ilog2(size_t(G));
-    const int log_n = ilog2(n), log_q = 1, q = 2;
+    const int log_n = ilog2(n), log_q = lsp_air_log_quotient_degree(n_lookups, n_cfgs), q = 1 << log_q;
     const int log_b = int(fri->log_blowup), log_l = log_n + log_b;
     if (log_q > log_b) return set_err(ctx, LSP_ERR_PARAM, "quotient degree 2^%d exceeds blowup 2^%d", log_q, log_b);
     if (log_g > log_b) return set_err(ctx, LSP_ERR_PARAM, "%d ranks need at least %d cosets (log_blowup >= %d)", G, G, log_g);
@@ -430,9 +431,6 @@ extern "C" int lsp_prove_permutation_sharded_dev(lsp_comm* cm, const lsp_fri_con
     if (fri->num_queries == 0 || fri->num_queries > 4096) return set_err(ctx, LSP_ERR_PARAM, "num_queries out of range");
     const size_t need = lsp_proof_words(log_n, uint32_t(W), log_q, fri);
     if (proof_words < need) return set_err(ctx, LSP_ERR_PARAM, "proof buffer too small: %zu < %zu words", proof_words, need);
-    size_t w_sum = 0;
-    for (int i = 0; i < n_cfgs; i++) w_sum += 2 * size_t(cfgs[i].n_cols) + 2;
-    if (w_sum != W) return set_err(ctx, LSP_ERR_PARAM, "AIR width %zu != trace width %zu", w_sum, W);
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
 
     const size_t L = size_t(1) << log_l, Lr = L >> log_g;
@@ -466,7 +464,7 @@ extern "C" int lsp_prove_permutation_sharded_dev(lsp_comm* cm, const lsp_fri_con
     // ---- replicated inputs: trace, coefficients, AIR config ---------------------------------------
     PermCfgDev cfg_dev;
     void* cfg_blob = nullptr;
-    LSP_TRY(upload_perm_cfgs(ctx, cfgs, n_cfgs, W, &cfg_dev, &cfg_blob));
+    LSP_TRY(upload_air_cfgs(ctx, lookups, n_lookups, cfgs, n_cfgs, W, &cfg_dev, &cfg_blob));
     P.ptrs.push_back(cfg_blob);
     Fr* coef_t = nullptr;
     LSP_TRY(P.get(&coef_t, n * W * 32));
@@ -740,13 +738,27 @@ extern "C" int lsp_prove_permutation_sharded_dev(lsp_comm* cm, const lsp_fri_con
     return LSP_OK;
 }
 
-extern "C" int lsp_prove_permutation_sharded(lsp_comm* cm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
-                                             const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out,
-                                             size_t proof_words, float* timings_ms_out) {
+extern "C" int lsp_prove_air_sharded(lsp_comm* cm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
+                                     const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* cfgs, int n_cfgs,
+                                     const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words, float* timings_ms_out) {
     if (!cm || !trace) return LSP_ERR_PARAM;
     lsp_mat* m = nullptr;
     LSP_TRY(lsp_mat_upload(cm->ctx, trace, rows, width, &m));
-    int rc = lsp_prove_permutation_sharded_dev(cm, fri, m, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
+    int rc = lsp_prove_air_sharded_dev(cm, fri, m, lookups, n_lookups, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
     lsp_mat_free(cm->ctx, m);
     return rc;
+}
+
+extern "C" int lsp_prove_permutation_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri, const lsp_mat* tr, const lsp_perm_air_cfg* cfgs,
+                                                 int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words,
+                                                 float* timings_ms_out) {
+    if (!cfgs || n_cfgs <= 0) return LSP_ERR_PARAM;
+    return lsp_prove_air_sharded_dev(cm, fri, tr, nullptr, 0, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
+}
+
+extern "C" int lsp_prove_permutation_sharded(lsp_comm* cm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
+                                             const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4], uint64_t* proof_out,
+                                             size_t proof_words, float* timings_ms_out) {
+    if (!cfgs || n_cfgs <= 0) return LSP_ERR_PARAM;
+    return lsp_prove_air_sharded(cm, fri, trace, rows, width, nullptr, 0, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
 }

@@ -166,3 +166,22 @@ def test_main_flow_cbor_files_to_proof(pkg, gctx, p2params):
     oproof = OS.prove(p2params, OS.FriConfig(**fri), cfgs, trace, [alpha, delta])
     assert gd == oproof
     OS.verify(p2params, OS.FriConfig(**fri), cfgs, gd, [alpha, delta])
+
+
+@pytest.mark.parametrize("log_n,lookups,perms,world,blowup", [(4, [(1, 1, 0)], [], 2, 2), (5, [(2, 2, 5)], [2], 4, 3), (6, [(1, 2, 0)], [1], 8, 3),
+                                                              (10, [(2, 1, 7)], [3], 2, 3)])
+def test_sharded_prove_of_lookup_air_equals_single_gpu(pkg, gctx, p2params, log_n, lookups, perms, world, blowup):
+    """The sharded prove with 4 quotient chunks (chunk owners spread over the ranks) on the local communicator."""
+    import numpy as np
+    cfgs, trace, publics = _instance(log_n, lookups, perms, 500 + log_n + world)
+    fri = pkg.FriConfig(log_blowup=blowup, num_queries=11)
+    g = _gpu_cfgs(pkg, cfgs)
+    single = pkg.prove(gctx, fri, g, trace, publics)
+    comm = pkg.Comm.local(gctx, world)
+    sharded = pkg.prove_sharded(comm, fri, g, trace, publics)
+    comm.close()
+    assert np.array_equal(single.words, sharded.words)
+    if log_n <= 6:
+        ofri = OS.FriConfig(log_blowup=blowup, num_queries=11)
+        gd, _ = sharded.to_dict()
+        assert gd == OS.prove(p2params, ofri, cfgs, trace, publics)
