@@ -291,9 +291,62 @@ static void coset_lde_cols(const fr* in, size_t n, int width, int added_bits, fr
 /* ---- AIR (air/src/lib.rs:116-167) ------------------------------------------------- */
 typedef struct { uint32_t n_cols; const uint32_t* a_ids; const uint32_t* b_ids; uint32_t b_inverse_id, check_id; } air_cfg;
 
+/* LogUp lookup configs (air/src/air_lookup.rs:2-11), registered with lsp_oracle_set_lookups before
+ * prove / verify: `LineaAIR::eval` folds them BEFORE the permutation configs (trace/src/lib.rs:80-89). */
+#define MAX_LK 8
+#define MAX_LK_IDS 64
+typedef struct { uint32_t n_a, n_t, n_b, a_filter, a_inv, check; uint32_t a_ids[MAX_LK_IDS]; uint32_t b_ids[MAX_LK_IDS];
+                 uint32_t b_filter[MAX_LK_IDS], b_inv[MAX_LK_IDS], occ[MAX_LK_IDS]; } lookup_cfg;
+static lookup_cfg LK[MAX_LK];
+static int N_LK = 0;
+
+/* blob per lookup: n_a, n_t, n_b, a_filter, a_inv, check, a_ids[n_a], then per table: b_filter, b_inv, occ, b_ids[n_b] */
+int lsp_oracle_set_lookups(const uint32_t* blob, int n_lookups) {
+    if (n_lookups < 0 || n_lookups > MAX_LK) return -1;
+    const uint32_t* r = blob;
+    for (int i = 0; i < n_lookups; i++) {
+        lookup_cfg* c = &LK[i];
+        c->n_a = r[0]; c->n_t = r[1]; c->n_b = r[2]; c->a_filter = r[3]; c->a_inv = r[4]; c->check = r[5];
+        if (c->n_a > MAX_LK_IDS || c->n_t * c->n_b > MAX_LK_IDS || c->n_t > MAX_LK_IDS) return -1;
+        r += 6;
+        for (uint32_t j = 0; j < c->n_a; j++) c->a_ids[j] = *r++;
+        for (uint32_t t = 0; t < c->n_t; t++) {
+            c->b_filter[t] = *r++; c->b_inv[t] = *r++; c->occ[t] = *r++;
+            for (uint32_t j = 0; j < c->n_b; j++) c->b_ids[t * c->n_b + j] = *r++;
+        }
+    }
+    N_LK = n_lookups;
+    return 0;
+}
+/* `get_log_quotient_degree`: a lookup's first-row constraint has degree 4 (=> 4 chunks), the permutation's 3 (=> 2) */
+static int air_log_q(void) { return N_LK > 0 ? 2 : 1; }
+
+/* eval_lookup (air/src/lib.rs:57-114), folded into acc */
+static fr fold_lookup(const lookup_cfg* l, fr acc, const fr* local, const fr* next, fr alpha_air, fr delta,
+                      fr is_first, fr is_last, fr is_trans, fr alpha) {
+    fr a_l = ZERO;
+    for (uint32_t j = 0; j < l->n_a; j++) a_l = fr_add(fr_mul(a_l, alpha_air), local[l->a_ids[j]]);
+    a_l = fr_add(a_l, delta);
+    acc = fr_add(fr_mul(acc, alpha), fr_sub(fr_mul(a_l, local[l->a_inv]), ONE));
+    fr chk_l = fr_mul(local[l->a_filter], local[l->a_inv]), chk_n = fr_mul(next[l->a_filter], next[l->a_inv]);
+    for (uint32_t t = 0; t < l->n_t; t++) {
+        fr b_l = ZERO;
+        for (uint32_t j = 0; j < l->n_b; j++) b_l = fr_add(fr_mul(b_l, alpha_air), local[l->b_ids[t * l->n_b + j]]);
+        b_l = fr_add(b_l, delta);
+        acc = fr_add(fr_mul(acc, alpha), fr_sub(fr_mul(b_l, local[l->b_inv[t]]), ONE));
+        chk_l = fr_sub(chk_l, fr_mul(fr_mul(local[l->b_filter[t]], local[l->occ[t]]), local[l->b_inv[t]]));
+        chk_n = fr_sub(chk_n, fr_mul(fr_mul(next[l->b_filter[t]], next[l->occ[t]]), next[l->b_inv[t]]));
+    }
+    acc = fr_add(fr_mul(acc, alpha), fr_mul(is_first, fr_sub(local[l->check], chk_l)));
+    acc = fr_add(fr_mul(acc, alpha), fr_mul(is_trans, fr_sub(fr_sub(next[l->check], local[l->check]), chk_n)));
+    acc = fr_add(fr_mul(acc, alpha), fr_mul(is_last, local[l->check]));
+    return acc;
+}
+
 static fr fold_constraints(const air_cfg* cfgs, int n_cfgs, const fr* local, const fr* next, fr alpha_air, fr delta,
                            fr is_first, fr is_last, fr is_trans, fr alpha) {
     fr acc = ZERO;
+    for (int k = 0; k < N_LK; k++) acc = fold_lookup(&LK[k], acc, local, next, alpha_air, delta, is_first, is_last, is_trans, alpha);
     for (int k = 0; k < n_cfgs; k++) {
         const air_cfg* p = &cfgs[k];
         fr a_l = ZERO, b_l = ZERO, a_n = ZERO;
@@ -369,7 +422,7 @@ int lsp_oracle_prove(const fri_cfg* fri, const uint64_t* trace_rm, size_t rows, 
     init_consts();
     if (!PP.set) return -3;
     const size_t n = rows, W = width;
-    const int log_n = ilog2(n), log_q = 1, q = 2, log_b = (int)fri->log_blowup, log_l = log_n + log_b;
+    const int log_n = ilog2(n), log_q = air_log_q(), q = 1 << log_q, log_b = (int)fri->log_blowup, log_l = log_n + log_b;
     if (((size_t)1 << log_n) != n || log_q > log_b || (int)fri->log_final_poly_len > log_n || log_b + (int)fri->log_final_poly_len > 10 || W > 250) return -1;
     const size_t L = (size_t)1 << log_l;
     const int n_rounds = log_n - (int)fri->log_final_poly_len, log_f = log_b + (int)fri->log_final_poly_len;
@@ -536,7 +589,7 @@ int lsp_oracle_verify(const fri_cfg* fri, uint32_t log_n, size_t width, const ai
                       const uint64_t* proof_in, size_t proof_words) {
     init_consts();
     if (!PP.set) return -3;
-    const size_t W = width; const int log_q = 1, q = 2, log_b = (int)fri->log_blowup, log_l = (int)log_n + log_b;
+    const size_t W = width; const int log_q = air_log_q(), q = 1 << log_q, log_b = (int)fri->log_blowup, log_l = (int)log_n + log_b;
     const int n_rounds = (int)log_n - (int)fri->log_final_poly_len, log_f = log_b + (int)fri->log_final_poly_len;
     if (proof_words != lsp_oracle_proof_words(log_n, (uint32_t)W, (uint32_t)log_q, fri)) return 1;
     const fr* proof = (const fr*)proof_in;

@@ -43,6 +43,7 @@ def load():
         lib.lsp_oracle_verify.argtypes = [C.POINTER(FriCfg), C.c_uint32, C.c_size_t, C.POINTER(AirCfg), C.c_int, u64p,
                                           u64p, C.c_size_t]
         lib.lsp_oracle_gen_trace.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]
+        lib.lsp_oracle_set_lookups.argtypes = [C.POINTER(C.c_uint32), C.c_int]
         _lib = lib
     return _lib
 
@@ -76,19 +77,38 @@ def fr_mul(a, b):
     return [from_mont_limbs(r) for r in out]
 
 
+def _is_lookup(c):
+    return hasattr(c, "occurrences_id")
+
+
 def c_cfgs(cfgs):
-    keep, arr = [], (AirCfg * len(cfgs))()
+    """Registers the lookup configs of a `LineaAIR` config list with the library (they are folded first,
+    trace/src/lib.rs:80-89) and returns the permutation configs as a C array.  Returns (array, keep-alive, log_q)."""
+    lookups = [c for c in cfgs if _is_lookup(c)]
+    cfgs = [c for c in cfgs if not _is_lookup(c)]
+    blob = []
+    for l in lookups:
+        blob += [len(l.a_columns_ids), len(l.b_columns_ids), len(l.b_columns_ids[0]), l.a_filter_id, l.a_inverses_id, l.check_id]
+        blob += list(l.a_columns_ids)
+        for t, ids in enumerate(l.b_columns_ids):
+            blob += [l.b_filter_id[t], l.b_inverses_id[t], l.occurrences_id[t]] + list(ids)
+    barr = (C.c_uint32 * max(1, len(blob)))(*blob)
+    if load().lsp_oracle_set_lookups(barr, len(lookups)) != 0:
+        raise RuntimeError("lookup configs too large for the C oracle")
+    keep, arr = [], (AirCfg * max(1, len(cfgs)))()
+    keep.append(2 if lookups else 1)
     for i, c in enumerate(cfgs):
         a = (C.c_uint32 * len(c.a_columns_ids))(*c.a_columns_ids)
         b = (C.c_uint32 * len(c.b_columns_ids))(*c.b_columns_ids)
         keep += [a, b]
         arr[i] = AirCfg(len(c.a_columns_ids), a, b, c.b_inverse_id, c.check_id)
+    keep.append(len(cfgs))
     return arr, keep
 
 
-def proof_words(log_n, width, fri):
+def proof_words(log_n, width, fri, log_q=1):
     f = FriCfg(fri.log_blowup, fri.log_final_poly_len, fri.num_queries, fri.proof_of_work_bits)
-    return int(load().lsp_oracle_proof_words(log_n, width, 1, C.byref(f)))
+    return int(load().lsp_oracle_proof_words(log_n, width, log_q, C.byref(f)))
 
 
 def prove_limbs(fri, trace_limbs: np.ndarray, n: int, w: int, cfgs, publics_limbs: np.ndarray, timings=None):
@@ -96,10 +116,10 @@ def prove_limbs(fri, trace_limbs: np.ndarray, n: int, w: int, cfgs, publics_limb
     in the same layout as the CUDA library (linea-stark-prover_b200/host/prover.cu)."""
     f = FriCfg(fri.log_blowup, fri.log_final_poly_len, fri.num_queries, fri.proof_of_work_bits)
     arr, keep = c_cfgs(cfgs)
-    words = proof_words(n.bit_length() - 1, w, fri)
+    words = proof_words(n.bit_length() - 1, w, fri, keep[0])
     out = np.zeros(words, dtype=np.uint64)
     tm = np.zeros(8, dtype=np.float64)
-    rc = load().lsp_oracle_prove(C.byref(f), _p(trace_limbs), n, w, arr, len(cfgs), _p(publics_limbs), _p(out), words,
+    rc = load().lsp_oracle_prove(C.byref(f), _p(trace_limbs), n, w, arr, keep[-1], _p(publics_limbs), _p(out), words,
                                  tm.ctypes.data_as(f64p))
     if rc != 0:
         raise RuntimeError(f"lsp_oracle_prove failed: {rc}")
@@ -118,7 +138,7 @@ def verify_limbs(fri, log_n: int, w: int, cfgs, publics_limbs: np.ndarray, proof
     """0 = accepted; otherwise the failing check (see lsp_oracle_verify)."""
     f = FriCfg(fri.log_blowup, fri.log_final_poly_len, fri.num_queries, fri.proof_of_work_bits)
     arr, keep = c_cfgs(cfgs)
-    rc = load().lsp_oracle_verify(C.byref(f), log_n, w, arr, len(cfgs), _p(publics_limbs),
+    rc = load().lsp_oracle_verify(C.byref(f), log_n, w, arr, keep[-1], _p(publics_limbs),
                                   _p(np.ascontiguousarray(proof_words_arr)), len(proof_words_arr))
     del keep
     return rc

@@ -185,3 +185,33 @@ def test_sharded_prove_of_lookup_air_equals_single_gpu(pkg, gctx, p2params, log_
         ofri = OS.FriConfig(log_blowup=blowup, num_queries=11)
         gd, _ = sharded.to_dict()
         assert gd == OS.prove(p2params, ofri, cfgs, trace, publics)
+
+
+def test_lookup_air_at_2p13_rows_matches_c_port(pkg, gctx, p2params):
+    """Beyond the Python oracle's reach: 2^13 rows, device witness == oracle witness, GPU proof == C port's proof,
+    accepted by the C verifier; a flipped multiplicity is rejected."""
+    import numpy as np
+    from oracle import cport
+    cport.set_poseidon2(p2params)
+    log_n, n = 13, 1 << 13
+    rng = F.SplitMix64(2024)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    a, b, af, bf = OT.synthetic_lookup_input(88, 2, 2, n, disabled_every=11)
+    cfg, cols = OT.lookup_columns(a, b, af, bf, alpha, delta)
+    pa, pb = OT.synthetic_permutation_input(89, 2, n)
+    cfgs, trace = OT.build_trace([(pa, pb)], alpha, delta, [(a, b, af, bf)])
+    pub = pkg.to_mont_array([alpha, delta])
+    t_lk = gctx.lookup_trace(pkg.to_mont_array(_lookup_rows(a, b, af, bf)), n, 2, 2, 2, pub)
+    ab = pkg.to_mont_array([x for i in range(n) for x in [c[i] for c in pa] + [c[i] for c in pb]])
+    dev = gctx.hconcat([t_lk, gctx.permutation_trace(ab, n, 2, pub)])
+    limbs = dev.download_array()
+    assert np.array_equal(limbs, pkg.to_mont_array([x for r in trace for x in r]))
+    fri = dict(log_blowup=3, log_final_poly_len=0, num_queries=33, proof_of_work_bits=0)
+    gproof = pkg.prove(gctx, pkg.FriConfig(**fri), _gpu_cfgs(pkg, cfgs), dev, [alpha, delta])
+    ofri = OS.FriConfig(**fri)
+    w = OA.air_width(cfgs)
+    assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, gproof.words) == 0
+    assert np.array_equal(cport.prove_limbs(ofri, limbs, n, w, cfgs, pub), gproof.words)
+    bad = gproof.words.copy()
+    bad[4 * (2 + cfgs[0].occurrences_id[0])] ^= 1
+    assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, bad) != 0

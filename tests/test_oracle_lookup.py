@@ -53,3 +53,35 @@ def test_prove_verify_lookup_and_permutation(p2params):
     proof["opened_values"]["trace_local"][cfgs[0].check_id] ^= 1
     with pytest.raises(OS.VerificationError):
         OS.verify(p2params, fri, cfgs, proof, [alpha, delta])
+
+
+@pytest.mark.parametrize("log_n,lookups,perms,fri", [
+    (3, [(1, 1, 0)], [], dict(log_blowup=2, log_final_poly_len=0, num_queries=5, proof_of_work_bits=0)),
+    (5, [(2, 2, 6), (1, 1, 0)], [2], dict(log_blowup=3, log_final_poly_len=1, num_queries=9, proof_of_work_bits=2)),
+])
+def test_c_port_proves_and_verifies_lookup_airs(p2params, log_n, lookups, perms, fri):
+    """The C port (oracle/c) pinned to the Python oracle on LineaAIRs with lookup configs: whole-proof equality."""
+    import numpy as np
+    from oracle import cport
+    from tests.proofs import flat_from_dict
+    cport.set_poseidon2(p2params)
+    n = 1 << log_n
+    rng = F.SplitMix64(log_n)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    lk = [OT.synthetic_lookup_input(30 + i, nc, nt, n, disabled_every=de) for i, (nc, nt, de) in enumerate(lookups)]
+    pm = [OT.synthetic_permutation_input(40 + i, c, n) for i, c in enumerate(perms)]
+    cfgs, trace = OT.build_trace(pm, alpha, delta, lk)
+    ofri = OS.FriConfig(**fri)
+    dbg = {}
+    pp = OS.prove(p2params, ofri, cfgs, trace, [alpha, delta], dbg)
+    words = cport.prove(ofri, cfgs, trace, [alpha, delta])
+    assert np.array_equal(words, flat_from_dict(pp, dbg["query_indices"]))
+    pub = np.array([F.to_mont_limbs(alpha), F.to_mont_limbs(delta)], dtype=np.uint64)
+    w = OA.air_width(cfgs)
+    assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, words) == 0
+    bad = words.copy()
+    bad[4 * (2 + cfgs[0].check_id)] ^= 1
+    assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, bad) != 0
+    # and the permutation-only path is unaffected by the registration above
+    cfgs2, trace2 = OT.build_trace([OT.synthetic_permutation_input(5, 2, 8)], alpha, delta)
+    assert cport.verify_limbs(ofri, 3, 6, cfgs2, pub, cport.prove(ofri, cfgs2, trace2, [alpha, delta])) == 0
