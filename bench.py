@@ -263,10 +263,12 @@ def run_gpu(args, rank, world, local_rank):
     for _ in range(args.warmup):
         prove_dev()
     # ---- timed region: `value` (trace resident in HBM) --------------------------------
+    # Only the dominant kernel (the Poseidon2 leaf hash: 2 launches per step) is bracketed by CUDA events here, on
+    # the library's own stream; events around every one of the ~400 launches would cost ~4 % of the step.
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ctx.kernel_launches()
-    ctx.kernel_timing(True)
+    ctx.kernel_timing(2)
     stage_acc = {}
     barrier()
     t0 = time.perf_counter()
@@ -280,6 +282,12 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     launches = (ctx.kernel_launches() - launches0) // args.steps
+    leaf_report = ctx.kernel_timing_report()     # the roofline's numerator: measured inside the timed region
+    # ---- every kernel's duration (top_kernels, shares): the same step again, fully instrumented ------
+    KSTEPS = 2
+    ctx.kernel_timing(True)
+    for _ in range(KSTEPS):
+        prove_dev()
     kernel_report = ctx.kernel_timing_report()
     ctx.kernel_timing(False)
     # device time of a step: CUDA events recorded by the library on ITS stream around every stage
@@ -310,8 +318,9 @@ def run_gpu(args, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel: Poseidon2 leaf hashing of the trace LDE -----
     big = (n << args.log_blowup) // world     # rows of the LDE hashed by this rank's leaf kernel
-    leaf = [r for r in kernel_report if r["phase"] == "commit_trace" and r["kernel"].startswith("k_leaf_hash")][0]
+    leaf = [r for r in leaf_report if r["phase"] == "commit_trace" and r["kernel"].startswith("k_leaf_hash")][0]
     leaf_ms = leaf["ms"] / leaf["launches"]
+    leaf_all = [r for r in kernel_report if r["phase"] == "commit_trace" and r["kernel"].startswith("k_leaf_hash")][0]
     leaf_bytes = big * w * 32 + big * 32
     hbm_peak, which = measured_peaks()
     achieved = leaf_bytes / (leaf_ms * 1e-3) / 1e9
@@ -327,7 +336,7 @@ def run_gpu(args, rank, world, local_rank):
         if t["rows"] == big and t["width"] == w:
             traffic = t["dram_bytes_per_launch"]
     tp, qp, fp = perm_counts(args.log_n, w, args.log_blowup, 2, 0)
-    kern_total = sum(r["ms"] for r in kernel_report) / args.steps
+    kern_total = sum(r["ms"] for r in kernel_report) / KSTEPS
     top = sorted(kernel_report, key=lambda r: -r["ms"])[:8]
 
     out = {
@@ -342,7 +351,7 @@ def run_gpu(args, rank, world, local_rank):
         "roofline": {"bound": "hbm", "kernel": "k_leaf_hash (trace LDE, %d rows x %d per launch)" % (big, w),
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": leaf_bytes, "peak_source": which, "ms_per_launch": leaf_ms,
-                     "share_of_step": leaf["ms"] / args.steps / kern_total,
+                     "share_of_step": leaf_all["ms"] / KSTEPS / kern_total,
                      "note": "integer-pipe bound kernel: see int_roofline for the binding fraction"},
         "int_roofline": {"bound": "int32 multiply (FMA-heavy) pipe", "achieved": int_ach, "peak": int_peak, "unit": "MAC32/s",
                          "frac": int_ach / int_peak, "imad_wide_per_perm": wide_per_perm,
@@ -351,8 +360,8 @@ def run_gpu(args, rank, world, local_rank):
                          "peak_source": "lsp_int_peak: independent data-dependent IMAD.WIDE.U32 chains timed on this device",
                          "note": "achieved counts the 32x32->64 products the launch executes (120 per product, 92 per "
                                  "square); cios_mac32_per_s is the same time against SURVEY's 136-MAC CIOS unit"},
-        "top_kernels": [{"phase": r["phase"], "kernel": r["kernel"], "launches": r["launches"] // args.steps,
-                         "ms": round(r["ms"] / args.steps, 3)} for r in top],
+        "top_kernels": [{"phase": r["phase"], "kernel": r["kernel"], "launches": r["launches"] // KSTEPS,
+                         "ms": round(r["ms"] / KSTEPS, 3)} for r in top],
         "e2e": {"value": e2e_wall_ms / 1e3, "unit": "s", "h2d_bytes_per_step": n * w * 32 * world,
                 "d2h_bytes_per_step": proof_bytes, "device_ms": e2e_dev / args.steps},
         "gpu_launches": int(launches),

@@ -51,8 +51,10 @@ int lsp_ctx_sync(lsp_ctx* ctx);
 /* Number of kernels this ctx has launched since creation (bench.py's gpu_launches). */
 uint64_t lsp_kernel_launches(const lsp_ctx* ctx);
 
-/* Per-kernel CUDA-event timing (off by default).  enable!=0 clears the records and starts
- * recording; the report is JSON [{"phase","kernel","launches","ms"},...]. */
+/* Per-kernel CUDA-event timing (off by default).  enable = 1 clears the records and times every
+ * launch (two events each: ~4 % on a 400-launch prove); enable = 2 times only the Poseidon2
+ * leaf-hash launches (the dominant kernel; free).  The report is JSON
+ * [{"phase","kernel","launches","ms"},...]. */
 int lsp_kernel_timing(lsp_ctx* ctx, int enable);
 int lsp_kernel_timing_report(lsp_ctx* ctx, char* buf, size_t cap);
 /* Measured issue rate of independent IMAD.WIDE.U32 (32x32+64 MACs per second) on this

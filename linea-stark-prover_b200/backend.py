@@ -75,8 +75,9 @@ class Context:
     def kernel_launches(self) -> int:
         return int(self.lib.lsp_kernel_launches(self.h))
 
-    def kernel_timing(self, enable: bool):
-        self.check(self.lib.lsp_kernel_timing(self.h, 1 if enable else 0), "lsp_kernel_timing")
+    def kernel_timing(self, enable):
+        """False/0: off; True/1: every launch; 2: only the leaf-hash launches (see lsp_kernel_timing)."""
+        self.check(self.lib.lsp_kernel_timing(self.h, int(enable)), "lsp_kernel_timing")
 
     def kernel_timing_report(self):
         import json

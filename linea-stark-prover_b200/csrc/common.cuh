@@ -30,6 +30,8 @@ struct lsp_ctx {
     size_t pinned_bytes = 0;
     // optional per-kernel timing (bench.py / profiles): CUDA events around every launch
     bool timing = false;
+    bool timing_leaf_only = false;   // mode 2: only the Poseidon2 leaf-hash launches (two events per commit)
+    bool timing_armed = false;       // set by timing_begin when it recorded e0 for the current launch
     const char* phase = "";
     struct TimingRec {
         const char* name;
@@ -96,14 +98,18 @@ inline cudaEvent_t timing_event(lsp_ctx* ctx) {
     return e;
 }
 inline void timing_begin(lsp_ctx* ctx, const char* name) {
+    ctx->timing_armed = false;
     if (!ctx->timing) return;
+    if (ctx->timing_leaf_only && !strstr(name, "k_leaf_hash")) return;
     lsp_ctx::TimingRec r{name, ctx->phase, timing_event(ctx), timing_event(ctx)};
     cudaEventRecord(r.e0, ctx->stream);
     ctx->timing_recs.push_back(r);
+    ctx->timing_armed = true;
 }
 inline void timing_end(lsp_ctx* ctx) {
-    if (!ctx->timing) return;
+    if (!ctx->timing_armed) return;
     cudaEventRecord(ctx->timing_recs.back().e1, ctx->stream);
+    ctx->timing_armed = false;
 }
 
 // Launch on the ctx stream, count it, and surface launch-time errors.

@@ -186,6 +186,7 @@ extern "C" int lsp_kernel_timing(lsp_ctx* ctx, int enable) {
     }
     ctx->timing_recs.clear();
     ctx->timing = enable != 0;
+    ctx->timing_leaf_only = enable == 2;
     return LSP_OK;
 }
 
