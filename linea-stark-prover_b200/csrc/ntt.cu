@@ -120,8 +120,13 @@ __global__ void __launch_bounds__(512) k_ntt_pass(const __grid_constant__ NttPas
             int i1 = i0 + (1 << lb);
             size_t g0 = base + (size_t(i0) << P.bit_lo);
             size_t e = (g0 & ((size_t(1) << b) - 1)) << (P.log_n - 1 - b);
-            Fr w = fr_load_nc(P.tw + e);
             Fr u = smem_get(plo, phi, i0), v = smem_get(plo, phi, i1);
+            if (b == 0) {  // the stage that pairs neighbours: every twiddle is w^0 = 1 (1/log2 n of all products)
+                smem_put(plo, phi, i0, fr_add(u, v));
+                smem_put(plo, phi, i1, fr_sub(u, v));
+                continue;
+            }
+            Fr w = fr_load_nc(P.tw + e);
             if (DIF) {
                 smem_put(plo, phi, i0, fr_add(u, v));
                 smem_put(plo, phi, i1, fr_mul(fr_sub(u, v), w));
