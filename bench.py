@@ -297,10 +297,13 @@ def run_gpu(args, rank, world, local_rank):
     barrier()
     t0 = time.perf_counter()
     e2e_dev = 0.0
+    e2e_stage = {}
     for _ in range(args.steps):
         tm = {}
         proof = prove_host(tm)
         e2e_dev += sum(tm.values())
+        for k, v in tm.items():
+            e2e_stage[k] = e2e_stage.get(k, 0.0) + v / args.steps
     barrier()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
     clocks = sampler.stop()
@@ -362,8 +365,9 @@ def run_gpu(args, rank, world, local_rank):
                                  "square); cios_mac32_per_s is the same time against SURVEY's 136-MAC CIOS unit"},
         "top_kernels": [{"phase": r["phase"], "kernel": r["kernel"], "launches": r["launches"] // KSTEPS,
                          "ms": round(r["ms"] / KSTEPS, 3)} for r in top],
-        "e2e": {"value": e2e_wall_ms / 1e3, "unit": "s", "h2d_bytes_per_step": n * w * 32 * world,
-                "d2h_bytes_per_step": proof_bytes, "device_ms": e2e_dev / args.steps},
+        "e2e": {"value": e2e_wall_ms / 1e3, "unit": "s", "h2d_bytes_per_step": n * w * 32,   # N > 1: every rank uploads its 1/N of the rows, NVLink all-gathers them
+                "d2h_bytes_per_step": proof_bytes, "device_ms": e2e_dev / args.steps,
+                "stages_ms": {k: round(v, 3) for k, v in e2e_stage.items()}},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

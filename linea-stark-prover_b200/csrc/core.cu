@@ -374,6 +374,13 @@ int lsp::mat_alloc(lsp_ctx* ctx, size_t rows, size_t width, lsp_mat** out) {
     return LSP_OK;
 }
 
+namespace lsp {
+int rowmajor_to_colmajor(lsp_ctx* ctx, const Fr* rm_dev, size_t rows, size_t width, Fr* cm_dev) {
+    LSP_LAUNCH(ctx, k_rm_to_cm, grid_for(ctx, rows * width, 256), 256, 0, rm_dev, cm_dev, rows, width, size_t(0), rows);
+    return LSP_OK;
+}
+}  // namespace lsp
+
 extern "C" int lsp_mat_upload(lsp_ctx* ctx, const uint64_t* rowmajor, size_t rows, size_t width, lsp_mat** out) {
     if (!ctx || !rowmajor || !out || rows == 0 || width == 0) return LSP_ERR_PARAM;
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));

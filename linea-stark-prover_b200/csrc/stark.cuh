@@ -41,6 +41,8 @@ int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width
                           int n_blocks, Fr* out, size_t out_col_stride);
 
 // ---- core.cu ---------------------------------------------------------------
+// device row-major (host layout) -> device column-major
+int rowmajor_to_colmajor(lsp_ctx* ctx, const Fr* rm_dev, size_t rows, size_t width, Fr* cm_dev);
 int merkle_build(lsp_ctx* ctx, const Fr* const* d_cols, int width, size_t h, Fr* digests);
 // digest layers over a vector viewed as rows of 2 (FRI commit-phase trees): layer0[j] = hash([v[2j], v[2j+1]])
 int merkle_build_pairs(lsp_ctx* ctx, const Fr* vec, size_t len, Fr* digests);

@@ -72,6 +72,10 @@ struct lsp_comm {
     int rank = 0;        // rank of this process (NCCL mode); unused in local mode
     bool local = false;  // all ranks hosted in this process on ctx's device
     ncclComm_t nccl = nullptr;
+    // reusable upload buffers of lsp_prove_air_sharded (row-major staging, column-major trace)
+    Fr* up_stage = nullptr;
+    Fr* up_mat = nullptr;
+    size_t up_elems = 0;
 };
 
 namespace {
@@ -410,6 +414,8 @@ extern "C" int lsp_comm_init_local(lsp_ctx* ctx, int world, lsp_comm** out) {
 extern "C" void lsp_comm_destroy(lsp_comm* cm) {
     if (!cm) return;
     if (cm->nccl && nccl_api()) nccl_api()->CommDestroy(cm->nccl);
+    cudaFree(cm->up_stage);
+    cudaFree(cm->up_mat);
     delete cm;
 }
 
@@ -738,15 +744,49 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     return LSP_OK;
 }
 
+// Host-trace entry point.  Over NCCL every rank uploads only ITS 1/G of the rows -- a contiguous slice of the
+// row-major host matrix, written at its place in a full-size row-major device buffer -- and an in-place
+// all-gather over NVLink completes the matrix: the trace crosses PCIe once in total instead of once per rank
+// (8 x 1 GiB at 2^22 rows).  Staging buffer and matrix belong to the communicator and are reused from call to
+// call, so this path leaves the stream-ordered pool -- and with it the prove's allocation pattern -- untouched.
 extern "C" int lsp_prove_air_sharded(lsp_comm* cm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows, size_t width,
                                      const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* cfgs, int n_cfgs,
                                      const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words, float* timings_ms_out) {
     if (!cm || !trace) return LSP_ERR_PARAM;
-    lsp_mat* m = nullptr;
-    LSP_TRY(lsp_mat_upload(cm->ctx, trace, rows, width, &m));
-    int rc = lsp_prove_air_sharded_dev(cm, fri, m, lookups, n_lookups, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
-    lsp_mat_free(cm->ctx, m);
-    return rc;
+    lsp_ctx* ctx = cm->ctx;
+    const size_t G = size_t(cm->world);
+    if (cm->local || G == 1 || rows % G != 0 || rows / G < 64) {
+        lsp_mat* m = nullptr;
+        LSP_TRY(lsp_mat_upload(ctx, trace, rows, width, &m));
+        int rc = lsp_prove_air_sharded_dev(cm, fri, m, lookups, n_lookups, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
+        lsp_mat_free(ctx, m);
+        return rc;
+    }
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t elems = rows * width, slice = rows / G;
+    if (cm->up_elems < elems) {
+        LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(cm->up_stage);
+        cudaFree(cm->up_mat);
+        cm->up_stage = cm->up_mat = nullptr;
+        cm->up_elems = 0;
+        LSP_CUDA(ctx, cudaMalloc((void**)&cm->up_stage, elems * 32));
+        LSP_CUDA(ctx, cudaMalloc((void**)&cm->up_mat, elems * 32));
+        cm->up_elems = elems;
+    }
+    Fr* mine = cm->up_stage + size_t(cm->rank) * slice * width;
+    LSP_CUDA(ctx, cudaMemcpyAsync(mine, trace + size_t(cm->rank) * slice * width * 4, slice * width * 32, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<int> ranks{cm->rank};
+    std::vector<const void*> send{mine};
+    std::vector<void*> recv{cm->up_stage};
+    LSP_TRY(coll_allgather(cm, ranks, send, recv, slice * width * 32));   // in place: send == recv + rank * count
+    LSP_TRY(rowmajor_to_colmajor(ctx, cm->up_stage, rows, width, cm->up_mat));
+    lsp_mat view;
+    view.d = cm->up_mat;
+    view.rows = rows;
+    view.width = width;
+    view.owns = false;
+    return lsp_prove_air_sharded_dev(cm, fri, &view, lookups, n_lookups, cfgs, n_cfgs, publics, proof_out, proof_words, timings_ms_out);
 }
 
 extern "C" int lsp_prove_permutation_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri, const lsp_mat* tr, const lsp_perm_air_cfg* cfgs,
