@@ -29,6 +29,7 @@ struct lsp_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     // optional per-kernel timing (bench.py / profiles): CUDA events around every launch
+    unsigned* grid_barrier = nullptr;   // arrival counter of the fused tree-top kernel
     bool timing = false;
     bool timing_leaf_only = false;   // mode 2: only the Poseidon2 leaf-hash launches (two events per commit)
     bool timing_armed = false;       // set by timing_begin when it recorded e0 for the current launch

@@ -104,6 +104,47 @@ __global__ void __launch_bounds__(32) k_compress_layer_tri(const __grid_constant
     if (live && w == 0) fr_store(out + i, s);
 }
 
+// The whole top of a tree in ONE launch: levels of <= 10 * gridDim.x nodes, three lanes per node, one warp per
+// block, a grid-wide barrier between levels (cooperative launch: every block is resident).  Level j reads
+// `in` and writes `out`; level j+1 reads that and writes right behind it (digest layers are stored back to
+// back).  Saves the ~7 us a separate launch costs per level on a chain of ~280 latency-bound levels per prove.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned target) {
+    __syncwarp();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        while (*(volatile unsigned*)counter < target) {
+        }
+        __threadfence();
+    }
+    __syncwarp();
+}
+template <int D>
+__global__ void __launch_bounds__(32) k_compress_top_tri(const __grid_constant__ P2Params P, const Fr* in, Fr* out, size_t n_out,
+                                                         int n_levels, unsigned* barrier) {
+    const int lane = threadIdx.x, k = lane / 3, w = lane - 3 * k;
+    for (int lvl = 0; lvl < n_levels; lvl++) {
+        size_t i = size_t(blockIdx.x) * 10 + k;
+        const bool live = k < 10 && i < n_out;
+        if (size_t(blockIdx.x) * 10 < n_out) {   // warp-uniform
+            if (!live) i = 0;
+            Fr s = fr_zero();
+            if (w < 2) {   // written by other blocks one level earlier: read through L2
+                const uint4* q = reinterpret_cast<const uint4*>(in + 2 * i + w);
+                uint4 a = __ldcg(q), b = __ldcg(q + 1);
+                s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
+                s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
+            }
+            p2_permute_tri<D>(P, s, w, 3 * k);
+            if (live && w == 0) fr_store(out + i, s);
+        }
+        if (lvl + 1 < n_levels) grid_barrier(barrier, unsigned(lvl + 1) * gridDim.x);
+        in = out;
+        out += n_out;
+        n_out >>= 1;
+    }
+}
+
 // Gather one row across columns (open_batch) into a contiguous buffer.
 __global__ void k_gather_row(const Fr* const* __restrict__ cols, int width, size_t row, Fr* __restrict__ out) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -163,6 +204,7 @@ extern "C" void lsp_ctx_destroy(lsp_ctx* ctx) {
     }
     for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaFree(ctx->grid_barrier);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -439,6 +481,31 @@ static int compress_layer(lsp_ctx* ctx, const Fr* in, Fr* out, size_t n_out) {
     return LSP_OK;
 }
 
+// Levels n_out, n_out/2, ..., 1 in one cooperative launch (n_out <= 10 warps x 4 sub-partitions x SMs).
+static int compress_top(lsp_ctx* ctx, const Fr* in, Fr* out, size_t n_out) {
+    int n_levels = ilog2(n_out) + 1;
+    if (n_levels == 1) return compress_layer(ctx, in, out, n_out);
+    if (!ctx->grid_barrier) LSP_CUDA(ctx, cudaMalloc((void**)&ctx->grid_barrier, 4));
+    LSP_CUDA(ctx, cudaMemsetAsync(ctx->grid_barrier, 0, 4, ctx->stream));
+    unsigned grid = unsigned((n_out + 9) / 10);
+    unsigned* bar = ctx->grid_barrier;
+    void* args[] = {(void*)&ctx->p2, (void*)&in, (void*)&out, (void*)&n_out, (void*)&n_levels, (void*)&bar};
+    lsp::timing_begin(ctx, "k_compress_top_tri<D>");
+    cudaError_t e = cudaErrorInvalidValue;
+    switch (ctx->p2.sbox_d) {
+        case 3: e = cudaLaunchCooperativeKernel((void*)k_compress_top_tri<3>, grid, 32, args, 0, ctx->stream); break;
+        case 5: e = cudaLaunchCooperativeKernel((void*)k_compress_top_tri<5>, grid, 32, args, 0, ctx->stream); break;
+        case 7: e = cudaLaunchCooperativeKernel((void*)k_compress_top_tri<7>, grid, 32, args, 0, ctx->stream); break;
+        case 11: e = cudaLaunchCooperativeKernel((void*)k_compress_top_tri<11>, grid, 32, args, 0, ctx->stream); break;
+        case 17: e = cudaLaunchCooperativeKernel((void*)k_compress_top_tri<17>, grid, 32, args, 0, ctx->stream); break;
+    }
+    lsp::timing_end(ctx);
+    ctx->launches++;
+    LSP_CUDA(ctx, e);
+    return LSP_OK;
+}
+static bool is_top(const lsp_ctx* ctx, size_t n_out) { return n_out <= size_t(ctx->sm_count) * 4 * 10 && is_pow2(n_out); }
+
 // digests must hold 2h-1 elements; cols is a device array of `width` column pointers.
 int merkle_build(lsp_ctx* ctx, const Fr* const* d_cols, int width, size_t h, Fr* digests) {
     if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
@@ -449,6 +516,7 @@ int merkle_build(lsp_ctx* ctx, const Fr* const* d_cols, int width, size_t h, Fr*
         size_t n_out = h >> (k + 1);
         const Fr* in = digests + tree_layer_offset(h, k);
         Fr* out = digests + tree_layer_offset(h, k + 1);
+        if (is_top(ctx, n_out)) return compress_top(ctx, in, out, n_out);   // this level and every one above it
         LSP_TRY(compress_layer(ctx, in, out, n_out));
     }
     return LSP_OK;
@@ -465,6 +533,7 @@ int merkle_build_pairs(lsp_ctx* ctx, const Fr* vec, size_t len, Fr* digests) {
     for (int k = 0; k <= log_h; k++) {
         size_t n_out = h >> k;
         Fr* out = digests + tree_layer_offset(h, k);
+        if (is_top(ctx, n_out)) return compress_top(ctx, in, out, n_out);
         LSP_TRY(compress_layer(ctx, in, out, n_out));
         in = out;
     }
