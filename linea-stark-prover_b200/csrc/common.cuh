@@ -133,6 +133,38 @@ inline void dev_free(lsp_ctx* ctx, void* p) {
     if (p) cudaFreeAsync(p, ctx->stream);
 }
 
+// Temporary device buffers of one call: everything handed out is returned to the stream-ordered pool when the
+// holder goes out of scope, on the success path and on every early return alike.
+struct Scratch {
+    lsp_ctx* ctx;
+    std::vector<void*> ptrs;
+    explicit Scratch(lsp_ctx* c) : ctx(c) {}
+    Scratch(const Scratch&) = delete;
+    Scratch& operator=(const Scratch&) = delete;
+    ~Scratch() {
+        for (void* p : ptrs) dev_free(ctx, p);
+    }
+    int get(void** p, size_t bytes) {
+        int rc = dev_alloc(ctx, p, bytes);
+        if (rc == LSP_OK) ptrs.push_back(*p);
+        return rc;
+    }
+};
+
+// A matrix under construction: freed on every early return, handed over with release().
+struct MatGuard {
+    lsp_ctx* ctx;
+    lsp_mat* m;
+    ~MatGuard() {
+        if (m) lsp_mat_free(ctx, m);
+    }
+    lsp_mat* release() {
+        lsp_mat* r = m;
+        m = nullptr;
+        return r;
+    }
+};
+
 inline int ilog2(size_t n) {
     int k = 0;
     while ((size_t(1) << k) < n) k++;

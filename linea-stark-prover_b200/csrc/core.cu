@@ -293,7 +293,8 @@ extern "C" int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s) {
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 8192;
     uint32_t* out = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&out, size_t(blocks) * threads * 4));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&out, size_t(blocks) * threads * 4));
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -310,7 +311,6 @@ extern "C" int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s) {
     ctx->launches += 6;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    dev_free(ctx, out);
     LSP_CUDA(ctx, cudaGetLastError());
     *mac32_per_s = double(blocks) * threads * iters * 8.0 / (best * 1e-3);
     return LSP_OK;
@@ -369,17 +369,15 @@ extern "C" int lsp_fr_op(lsp_ctx* ctx, int op, const uint64_t* a, const uint64_t
     if (n == 0) return LSP_OK;
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
     Fr *da = nullptr, *db = nullptr, *dout = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&da, n * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&db, n * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&dout, n * 32));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&da, n * 32));
+    LSP_TRY(tmp.get((void**)&db, n * 32));
+    LSP_TRY(tmp.get((void**)&dout, n * 32));
     LSP_CUDA(ctx, cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     if (op <= 2) LSP_CUDA(ctx, cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, ctx->stream));
     LSP_LAUNCH(ctx, k_fr_op, grid_for(ctx, n, 128), 128, 0, op, da, db, dout, n);
     LSP_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, da);
-    dev_free(ctx, db);
-    dev_free(ctx, dout);
     return LSP_OK;
 }
 
@@ -389,14 +387,13 @@ extern "C" int lsp_poseidon2_permute(lsp_ctx* ctx, const uint64_t* in, uint64_t*
     if (n == 0) return LSP_OK;
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
     Fr *din = nullptr, *dout = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&din, n * 96));
-    LSP_TRY(dev_alloc(ctx, (void**)&dout, n * 96));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&din, n * 96));
+    LSP_TRY(tmp.get((void**)&dout, n * 96));
     LSP_CUDA(ctx, cudaMemcpyAsync(din, in, n * 96, cudaMemcpyHostToDevice, ctx->stream));
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_p2_permute<D>, grid_for(ctx, n, 128), 128, 0, ctx->p2, din, dout, n));
     LSP_CUDA(ctx, cudaMemcpyAsync(out, dout, n * 96, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, din);
-    dev_free(ctx, dout);
     return LSP_OK;
 }
 
@@ -429,10 +426,10 @@ extern "C" int lsp_mat_upload(lsp_ctx* ctx, const uint64_t* rowmajor, size_t row
     lsp_mat* m = nullptr;
     LSP_TRY(mat_alloc(ctx, rows, width, &m));
     Fr* stage = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&stage, rows * width * 32));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&stage, rows * width * 32));
     LSP_CUDA(ctx, cudaMemcpyAsync(stage, rowmajor, rows * width * 32, cudaMemcpyHostToDevice, ctx->stream));
     LSP_LAUNCH(ctx, k_rm_to_cm, grid_for(ctx, rows * width, 256), 256, 0, stage, m->d, rows, width, size_t(0), rows);
-    dev_free(ctx, stage);
     *out = m;
     return LSP_OK;
 }
@@ -442,11 +439,11 @@ extern "C" int lsp_mat_download_rows(lsp_ctx* ctx, const lsp_mat* m, size_t row0
     if (nrows == 0) return LSP_OK;
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
     Fr* stage = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&stage, nrows * m->width * 32));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&stage, nrows * m->width * 32));
     LSP_LAUNCH(ctx, k_cm_to_rm, grid_for(ctx, nrows * m->width, 256), 256, 0, m->d, stage, m->rows, m->width, row0, nrows);
     LSP_CUDA(ctx, cudaMemcpyAsync(out, stage, nrows * m->width * 32, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, stage);
     return LSP_OK;
 }
 
@@ -585,7 +582,8 @@ extern "C" int lsp_merkle_open_batch(lsp_ctx* ctx, const lsp_tree* t, size_t ind
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
     Fr* buf = nullptr;
     size_t n = t->total_width + t->log_h;
-    LSP_TRY(dev_alloc(ctx, (void**)&buf, n * 32));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&buf, n * 32));
     LSP_LAUNCH(ctx, k_gather_row, unsigned((t->total_width + 63) / 64), 64, 0, t->d_cols, int(t->total_width), index, buf);
     if (t->log_h > 0)
         LSP_LAUNCH(ctx, k_gather_siblings, 1, 64, 0, t->digests, t->height, t->log_h, index, buf + t->total_width);
@@ -593,7 +591,6 @@ extern "C" int lsp_merkle_open_batch(lsp_ctx* ctx, const lsp_tree* t, size_t ind
     if (t->log_h > 0)
         LSP_CUDA(ctx, cudaMemcpyAsync(siblings_out, buf + t->total_width, size_t(t->log_h) * 32, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, buf);
     return LSP_OK;
 }
 
@@ -630,16 +627,15 @@ extern "C" int lsp_hash_rows(lsp_ctx* ctx, const uint64_t* rowmajor, size_t rows
     for (size_t c = 0; c < width; c++) cols.push_back(m->d + c * rows);
     const Fr** d_cols = nullptr;
     Fr* dig = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&d_cols, cols.size() * sizeof(Fr*)));
-    LSP_TRY(dev_alloc(ctx, (void**)&dig, rows * 32));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&d_cols, cols.size() * sizeof(Fr*)));
+    LSP_TRY(tmp.get((void**)&dig, rows * 32));
     LSP_CUDA(ctx, cudaMemcpyAsync(d_cols, cols.data(), cols.size() * sizeof(Fr*), cudaMemcpyHostToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_leaf_hash<D>, grid_for(ctx, rows, 128, LSP_P2_MINB), 128, 0, ctx->p2,
                                                  (const Fr* const*)d_cols, int(width), rows, dig));
     LSP_CUDA(ctx, cudaMemcpyAsync(digests_out, dig, rows * 32, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, (void*)d_cols);
-    dev_free(ctx, dig);
     lsp_mat_free(ctx, m);
     return LSP_OK;
 }

@@ -260,8 +260,9 @@ int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width
     int lo_bits = log_n < 10 ? log_n : 10;
     size_t n_lo = size_t(1) << lo_bits, n_hi = size_t(1) << (log_n - lo_bits);
     Fr *pow_lo = nullptr, *pow_hi = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&pow_lo, n_blocks * n_lo * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&pow_hi, n_blocks * n_hi * 32));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&pow_lo, n_blocks * n_lo * 32));
+    LSP_TRY(tmp.get((void**)&pow_hi, n_blocks * n_hi * 32));
     {
         dim3 grid((unsigned)((n_lo + n_hi + 127) / 128), (unsigned)n_blocks);
         LSP_LAUNCH(ctx, k_coset_pow_tables, grid, 128, 0, pow_lo, pow_hi, shift, log_n, added_bits, lo_bits, block0);
@@ -294,8 +295,6 @@ int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width
         P.t = ts[p];
         LSP_TRY(launch_pass(ctx, true, P, width, n_blocks));
     }
-    dev_free(ctx, pow_lo);
-    dev_free(ctx, pow_hi);
     return LSP_OK;
 }
 

@@ -147,7 +147,8 @@ int challenger_sample_bits(lsp_ctx* ctx, DevChallenger* ch, int bits, int n, uin
 }
 int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out) {
     unsigned long long* best = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&best, 8));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&best, 8));
     if (bits == 0) {
         LSP_CUDA(ctx, cudaMemsetAsync(best, 0, 8, ctx->stream));  // witness 0 always passes
     } else {
@@ -165,7 +166,6 @@ int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out)
         }
     }
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_apply_witness<D>, 1, 32, 0, ctx->p2, ch, (const unsigned long long*)best, witness_out));
-    dev_free(ctx, best);
     return LSP_OK;
 }
 
@@ -332,7 +332,8 @@ int inverse_denominators_range(lsp_ctx* ctx, const Fr* z_dev, int n_points, int 
     const Fr* tw = nullptr;
     LSP_TRY(twiddles(ctx, log_m, false, &tw));
     InvDenScalars* S = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&S, sizeof(InvDenScalars) * n_points));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&S, sizeof(InvDenScalars) * n_points));
     LSP_LAUNCH(ctx, k_invden_setup, 1, n_points, 0, z_dev, log_m, S);
     int la = log_m < 10 ? log_m : 10;
     int lb = log_m - 3 > la ? log_m - 3 : la;
@@ -341,7 +342,7 @@ int inverse_denominators_range(lsp_ctx* ctx, const Fr* z_dev, int n_points, int 
     if (!direct && ((p0 | count) & ((size_t(1) << depth) - 1)))
         return set_err(ctx, LSP_ERR_PARAM, "inverse_denominators: range must be aligned to %d rows", 1 << depth);
     Fr* top = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&top, (size_t(1) << la) * 32));
+    LSP_TRY(tmp.get((void**)&top, (size_t(1) << la) * 32));
     for (int p = 0; p < n_points; p++) {
         LSP_LAUNCH(ctx, k_invden_top, unsigned(((size_t(1) << la) + 127) / 128), 128, 0, S + p, tw, log_m, la, top);
         if (direct) {
@@ -352,8 +353,6 @@ int inverse_denominators_range(lsp_ctx* ctx, const Fr* z_dev, int n_points, int 
                        p0 >> depth, n_nodes);
         }
     }
-    dev_free(ctx, top);
-    dev_free(ctx, S);
     return LSP_OK;
 }
 
@@ -519,7 +518,8 @@ int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, siz
         return set_err(ctx, LSP_ERR_PARAM, "quotient range must cover whole chunks");
     Fr* scal = nullptr;  // zh[2q], w_n_inv, pts[2]
     size_t q = size_t(1) << log_q;
-    LSP_TRY(dev_alloc(ctx, (void**)&scal, (2 * q + 3) * 32));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&scal, (2 * q + 3) * 32));
     Fr *zh = scal, *w_n_inv = scal + 2 * q, *pts = scal + 2 * q + 1;
     LSP_LAUNCH(ctx, k_quotient_setup, 1, unsigned(q < 32 ? 32 : q), 0, log_n, log_q, zh, w_n_inv, pts);
     Fr* inv[2] = {nullptr, nullptr};
@@ -548,7 +548,6 @@ int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, siz
     LSP_LAUNCH(ctx, k_quotient_permutation, grid_for(ctx, count, 128), 128, 0, A);
     dev_free(ctx, inv[0]);
     dev_free(ctx, inv[1]);
-    dev_free(ctx, scal);
     return LSP_OK;
 }
 
@@ -635,19 +634,18 @@ int eval_columns_at(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, cons
     int lo_bits = log_n < EVAL_LO_BITS ? log_n : EVAL_LO_BITS;
     size_t n_lo = size_t(1) << lo_bits, n_hi = size_t(1) << (log_n - lo_bits);
     Fr* tab = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&tab, (n_lo + n_hi) * 32));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&tab, (n_lo + n_hi) * 32));
     LSP_LAUNCH(ctx, k_point_pow_tables, unsigned((n_lo + n_hi + 127) / 128), 128, 0, z_dev, log_n, lo_bits, tab, tab + n_lo);
     int groups = int((width + EVAL_COLS - 1) / EVAL_COLS);
     int blocks = int((n + EVAL_THREADS - 1) / EVAL_THREADS);
     int cap = ctx->sm_count * 4;
     if (blocks > cap) blocks = cap;
     Fr* partial = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&partial, size_t(groups) * blocks * EVAL_COLS * 32));
+    LSP_TRY(tmp.get((void**)&partial, size_t(groups) * blocks * EVAL_COLS * 32));
     LSP_LAUNCH(ctx, k_eval_partial, dim3(blocks, groups), EVAL_THREADS, 0, coeffs, n, int(width), lo_bits, (const Fr*)tab,
                (const Fr*)(tab + n_lo), partial);
     LSP_LAUNCH(ctx, k_eval_finish, unsigned((width + 63) / 64), 64, 0, (const Fr*)partial, blocks, int(width), y_dev);
-    dev_free(ctx, partial);
-    dev_free(ctx, tab);
     return LSP_OK;
 }
 

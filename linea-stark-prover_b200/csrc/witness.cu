@@ -324,12 +324,14 @@ static int permutation_trace_impl(lsp_ctx* ctx, const void* ab_rowmajor, bool bi
     Fr *stage = nullptr, *pub = nullptr, *totals = nullptr;
     int* flag = nullptr;
     const size_t n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-    LSP_TRY(dev_alloc(ctx, (void**)&stage, n * w_in * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&pub, 64));
-    LSP_TRY(dev_alloc(ctx, (void**)&totals, n_tiles * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&flag, 4));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&stage, n * w_in * 32));
+    LSP_TRY(tmp.get((void**)&pub, 64));
+    LSP_TRY(tmp.get((void**)&totals, n_tiles * 32));
+    LSP_TRY(tmp.get((void**)&flag, 4));
     lsp_mat* m = nullptr;
     LSP_TRY(mat_alloc(ctx, n, w_out, &m));
+    MatGuard m_guard{ctx, m};   // released unless handed to the caller
     LSP_CUDA(ctx, cudaMemcpyAsync(stage, ab_rowmajor, n * w_in * 32, cudaMemcpyHostToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaMemcpyAsync(pub, publics, 64, cudaMemcpyHostToDevice, ctx->stream));
     if (big_endian_bytes) LSP_LAUNCH(ctx, k_be_to_mont, grid_for(ctx, n * w_in, 128), 128, 0, stage, n * w_in);
@@ -343,15 +345,9 @@ static int permutation_trace_impl(lsp_ctx* ctx, const void* ab_rowmajor, bool bi
     LSP_LAUNCH(ctx, k_check_last_is_one, 1, 1, 0, (const Fr*)num, n, flag);
     LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    dev_free(ctx, stage);
-    dev_free(ctx, pub);
-    dev_free(ctx, totals);
-    dev_free(ctx, flag);
-    if (*(volatile int*)ctx->pinned) {
-        lsp_mat_free(ctx, m);
+    if (*(volatile int*)ctx->pinned)
         return set_err(ctx, LSP_ERR_PARAM, "failed to check constrain: check column should be 1 on the last row");
-    }
-    *trace_out = m;
+    *trace_out = m_guard.release();
     return LSP_OK;
 }
 
@@ -368,17 +364,19 @@ static int lookup_trace_impl(lsp_ctx* ctx, const void* in_rowmajor, bool big_end
     int *flag = nullptr, *rep = nullptr;
     unsigned* count = nullptr;
     unsigned long long* first = nullptr;
-    LSP_TRY(dev_alloc(ctx, (void**)&stage, n * w_in * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&pub, 64));
-    LSP_TRY(dev_alloc(ctx, (void**)&totals, n_tiles * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&a_key, n * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&b_key, n * n_t * 32));
-    LSP_TRY(dev_alloc(ctx, (void**)&flag, 4));
-    LSP_TRY(dev_alloc(ctx, (void**)&rep, cap * 4));
-    LSP_TRY(dev_alloc(ctx, (void**)&count, cap * 4));
-    LSP_TRY(dev_alloc(ctx, (void**)&first, cap * 8));
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&stage, n * w_in * 32));
+    LSP_TRY(tmp.get((void**)&pub, 64));
+    LSP_TRY(tmp.get((void**)&totals, n_tiles * 32));
+    LSP_TRY(tmp.get((void**)&a_key, n * 32));
+    LSP_TRY(tmp.get((void**)&b_key, n * n_t * 32));
+    LSP_TRY(tmp.get((void**)&flag, 4));
+    LSP_TRY(tmp.get((void**)&rep, cap * 4));
+    LSP_TRY(tmp.get((void**)&count, cap * 4));
+    LSP_TRY(tmp.get((void**)&first, cap * 8));
     lsp_mat* m = nullptr;
     LSP_TRY(mat_alloc(ctx, n, w_out, &m));
+    MatGuard m_guard{ctx, m};   // released unless handed to the caller
     LSP_CUDA(ctx, cudaMemcpyAsync(stage, in_rowmajor, n * w_in * 32, cudaMemcpyHostToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaMemcpyAsync(pub, publics, 64, cudaMemcpyHostToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaMemsetAsync(rep, 0xff, cap * 4, ctx->stream));
@@ -414,13 +412,9 @@ static int lookup_trace_impl(lsp_ctx* ctx, const void* in_rowmajor, bool big_end
     LSP_LAUNCH(ctx, k_check_last_is_zero, 1, 1, 0, (const Fr*)prefix, n, flag);
     LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    for (void* q : {(void*)stage, (void*)pub, (void*)totals, (void*)a_key, (void*)b_key, (void*)flag, (void*)rep, (void*)count, (void*)first})
-        dev_free(ctx, q);
-    if (*(volatile int*)ctx->pinned) {
-        lsp_mat_free(ctx, m);
+    if (*(volatile int*)ctx->pinned)
         return set_err(ctx, LSP_ERR_PARAM, "failed to check constrain: check column should be 0 on the last row");
-    }
-    *trace_out = m;
+    *trace_out = m_guard.release();
     return LSP_OK;
 }
 

@@ -202,20 +202,6 @@ Fr host_pow2_inverse(int k) {
     return r;
 }
 
-struct Scratch {  // frees everything it handed out when the prove call returns
-    lsp_ctx* ctx;
-    std::vector<void*> ptrs;
-    explicit Scratch(lsp_ctx* c) : ctx(c) {}
-    ~Scratch() {
-        for (void* p : ptrs) dev_free(ctx, p);
-    }
-    int get(void** p, size_t bytes) {
-        int rc = dev_alloc(ctx, p, bytes);
-        if (rc == LSP_OK) ptrs.push_back(*p);
-        return rc;
-    }
-};
-
 int max_constraint_log_quotient(int n_lookups, int /*n_perms*/) {
     // `get_log_quotient_degree`, log2_ceil(max degree - 1):
     //   permutation AIR: max degree 3 (is_first_row * (check - a_ch * inv), air/src/lib.rs:146-148)      => 1
