@@ -7,6 +7,7 @@
 #include "fr.cuh"
 #include "fr29.cuh"
 #include "fr_mul_v1.cuh"
+#include "fr_mul_split.cuh"
 
 using namespace lsp;
 #define CHAINS 2
@@ -38,6 +39,7 @@ __global__ void __launch_bounds__(128) k(const Fr* __restrict__ in, Fr* __restri
                 if (MODE == 1) x[c] = fr_mul(x[c], y[c]);
                 if (MODE == 4) x[c] = lsp_v1::fr_mul_v1(x[c], x[c]);
                 if (MODE == 5) x[c] = fr_sqr(x[c]);
+                if (MODE == 7) x[c] = lsp_split::fr_mul_split(x[c], y[c]);
                 if (MODE == 2) x[c] = f29_pack_lazy(f29_mul(f29_unpack(x[c]), f29_unpack(y[c])));
             }
         }
@@ -97,6 +99,10 @@ int main() {
     check("f29 packed", o1);
     run<3>("f29 persistent", in, o1, n, blocks);
     check("f29 persistent", o1);
+    run<0>("fr_mul_v1 (again, reference)", in, o0, n, blocks);
+    cudaMemcpy(a, o0, out_n * sizeof(Fr), cudaMemcpyDeviceToHost);
+    run<7>("fr_mul_split (mul-only + adds)", in, o1, n, blocks);
+    check("fr_mul_split", o1);
     run<4>("v1 x*x chain", in, o0, n, blocks);
     cudaMemcpy(a, o0, out_n * sizeof(Fr), cudaMemcpyDeviceToHost);
     run<5>("fr_sqr (92 IMAD.WIDE)", in, o1, n, blocks);
