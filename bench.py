@@ -370,6 +370,10 @@ def run_gpu(args, rank, world, local_rank):
                 "stages_ms": {k: round(v, 3) for k, v in e2e_stage.items()}},
         "gpu_launches": int(launches),
         "clocks": clocks,
+        # context only (vs_baseline stays null: BASELINE.json publishes no B200 number for this metric)
+        "reference_published": {"value": 330.0, "unit": "s", "what": "the reference's own CPU prove of its README workload "
+                                "(14-column trace, 8 quotient chunks)", "hardware": "x86-64, 18 of 24 CPUs online",
+                                "source": "reference README.md:11,19-21; bench.log:18 (342 s)"},
     }
     if world == 1 and not args.no_cpu_baseline:
         fri_kw = dict(log_blowup=args.log_blowup, log_final_poly_len=0, num_queries=33, proof_of_work_bits=0)
