@@ -19,6 +19,7 @@
 // `lsp_comm_init_local` instead hosts all G ranks in ONE process on ONE device, running the
 // ranks' stages in lockstep and replacing every collective by device copies: the same code
 // path, testable on a single GPU (and what the 1-GPU CI box exercises).
+#include <algorithm>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -476,7 +477,24 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     LSP_TRY(P.get(&coef_t, n * W * 32));
     mark();  // 0
     ctx->phase = "commit_trace";
-    LSP_TRY(interpolate_columns(ctx, tr->d, n, W, coef_t));
+    if (!cm->local && G > 1) {
+        // Every rank needs all coefficients, but not to compute them all: each interpolates its slice of the columns
+        // and the slices are broadcast over NVLink (W*N*32 bytes in total) instead of G redundant inverse NTTs.
+        const size_t per = (W + size_t(G) - 1) / size_t(G);
+        for (int r = 0; r < G; r++) {
+            const size_t c0 = std::min(W, size_t(r) * per), c1 = std::min(W, c0 + per);
+            if (c1 == c0) continue;
+            if (r == cm->rank) LSP_TRY(interpolate_columns(ctx, tr->d + c0 * n, n, c1 - c0, coef_t + c0 * n));
+        }
+        for (int r = 0; r < G; r++) {
+            const size_t c0 = std::min(W, size_t(r) * per), c1 = std::min(W, c0 + per);
+            if (c1 == c0) continue;
+            std::vector<void*> buf{coef_t + c0 * n};
+            LSP_TRY(coll_broadcast(cm, ranks, r, buf, (c1 - c0) * n * 32));
+        }
+    } else {
+        LSP_TRY(interpolate_columns(ctx, tr->d, n, W, coef_t));
+    }
 
     std::vector<RankState> st(H);
     for (size_t i = 0; i < H; i++) {
