@@ -620,13 +620,37 @@ __global__ void __launch_bounds__(EVAL_THREADS) k_eval_partial(const Fr* __restr
         __syncthreads();
     }
 }
-__global__ void k_eval_finish(const Fr* __restrict__ partial, int n_blocks, int width, Fr* __restrict__ y) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
+// One block per column: the n_blocks partial sums are added by 128 threads and a shared-memory tree (a single thread
+// walking them one dependent global load at a time took 0.28 ms per call, four calls per prove).
+__global__ void __launch_bounds__(EVAL_THREADS) k_eval_finish(const Fr* __restrict__ partial, int n_blocks, int width, Fr* __restrict__ y) {
+    __shared__ uint4 red[EVAL_THREADS * 2];
+    const int c = blockIdx.x;
     if (c >= width) return;
-    int grp = c / EVAL_COLS, cc = c % EVAL_COLS;
+    const int grp = c / EVAL_COLS, cc = c % EVAL_COLS;
     Fr acc = fr_zero();
-    for (int b = 0; b < n_blocks; b++) acc = fr_add(acc, fr_load(partial + (size_t(grp) * n_blocks + b) * EVAL_COLS + cc));
-    fr_store(y + c, acc);
+    for (int b = threadIdx.x; b < n_blocks; b += EVAL_THREADS) acc = fr_add(acc, fr_load_nc(partial + (size_t(grp) * n_blocks + b) * EVAL_COLS + cc));
+    red[threadIdx.x] = make_uint4(acc.l[0], acc.l[1], acc.l[2], acc.l[3]);
+    red[EVAL_THREADS + threadIdx.x] = make_uint4(acc.l[4], acc.l[5], acc.l[6], acc.l[7]);
+    __syncthreads();
+    for (int s = EVAL_THREADS / 2; s > 0; s >>= 1) {
+        if (threadIdx.x < s) {
+            uint4 a0 = red[threadIdx.x], a1 = red[EVAL_THREADS + threadIdx.x];
+            uint4 b0 = red[threadIdx.x + s], b1 = red[EVAL_THREADS + threadIdx.x + s];
+            Fr a, b;
+            a.l[0] = a0.x; a.l[1] = a0.y; a.l[2] = a0.z; a.l[3] = a0.w; a.l[4] = a1.x; a.l[5] = a1.y; a.l[6] = a1.z; a.l[7] = a1.w;
+            b.l[0] = b0.x; b.l[1] = b0.y; b.l[2] = b0.z; b.l[3] = b0.w; b.l[4] = b1.x; b.l[5] = b1.y; b.l[6] = b1.z; b.l[7] = b1.w;
+            a = fr_add(a, b);
+            red[threadIdx.x] = make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]);
+            red[EVAL_THREADS + threadIdx.x] = make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        uint4 a0 = red[0], a1 = red[EVAL_THREADS];
+        Fr a;
+        a.l[0] = a0.x; a.l[1] = a0.y; a.l[2] = a0.z; a.l[3] = a0.w; a.l[4] = a1.x; a.l[5] = a1.y; a.l[6] = a1.z; a.l[7] = a1.w;
+        fr_store(y + c, a);
+    }
 }
 
 int eval_columns_at(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, const Fr* z_dev, Fr* y_dev) {
@@ -645,7 +669,7 @@ int eval_columns_at(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, cons
     LSP_TRY(tmp.get((void**)&partial, size_t(groups) * blocks * EVAL_COLS * 32));
     LSP_LAUNCH(ctx, k_eval_partial, dim3(blocks, groups), EVAL_THREADS, 0, coeffs, n, int(width), lo_bits, (const Fr*)tab,
                (const Fr*)(tab + n_lo), partial);
-    LSP_LAUNCH(ctx, k_eval_finish, unsigned((width + 63) / 64), 64, 0, (const Fr*)partial, blocks, int(width), y_dev);
+    LSP_LAUNCH(ctx, k_eval_finish, unsigned(width), EVAL_THREADS, 0, (const Fr*)partial, blocks, int(width), y_dev);
     return LSP_OK;
 }
 
