@@ -5,6 +5,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/lsp_b200.h"
@@ -30,6 +31,11 @@ struct lsp_ctx {
     size_t pinned_bytes = 0;
     // optional per-kernel timing (bench.py / profiles): CUDA events around every launch
     unsigned* grid_barrier = nullptr;   // arrival counter of the fused tree-top kernel
+    // shape-only selector tables of the quotient kernel, keyed by (log_n, log_q, first row, rows)
+    struct QuotSel {
+        lsp::Fr *scal = nullptr, *inv0 = nullptr, *inv1 = nullptr;
+    };
+    std::map<std::tuple<int, int, size_t, size_t>, QuotSel> quot_sel;
     bool timing = false;
     bool timing_leaf_only = false;   // mode 2: only the Poseidon2 leaf-hash launches (two events per commit)
     bool timing_armed = false;       // set by timing_begin when it recorded e0 for the current launch

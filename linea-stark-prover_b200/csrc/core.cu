@@ -205,6 +205,11 @@ extern "C" void lsp_ctx_destroy(lsp_ctx* ctx) {
     for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaFree(ctx->grid_barrier);
+    for (auto& kv : ctx->quot_sel) {
+        cudaFree(kv.second.scal);
+        cudaFree(kv.second.inv0);
+        cudaFree(kv.second.inv1);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
