@@ -319,6 +319,17 @@ def run_gpu(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    # ---- `verify` (main.rs:88-96) of the last proof on the device: reported beside the metric, not part of it ----
+    vt = {}
+    pkg.verify(ctx, fri, cfgs, proof, publics_ints)          # raises if the proof is not accepted
+    t0v = time.perf_counter()
+    VSTEPS = 5
+    for _ in range(VSTEPS):
+        pkg.verify(ctx, fri, cfgs, proof, publics_ints, timing=vt)
+    verify_info = {"accepted": True, "wall_ms": (time.perf_counter() - t0v) * 1e3 / VSTEPS, "device_ms": vt["device_ms"],
+                   "what": "lsp_verify_air: transcript replay, proof of work, 33 queries x 21 Merkle paths + fold chains, "
+                           "out-of-domain check; proof uploaded from host inside the timed call"}
+
     # ---- roofline of the dominant kernel: Poseidon2 leaf hashing of the trace LDE -----
     big = (n << args.log_blowup) // world     # rows of the LDE hashed by this rank's leaf kernel
     leaf = [r for r in leaf_report if r["phase"] == "commit_trace" and r["kernel"].startswith("k_leaf_hash")][0]
@@ -369,6 +380,7 @@ def run_gpu(args, rank, world, local_rank):
                 "d2h_bytes_per_step": proof_bytes, "device_ms": e2e_dev / args.steps,
                 "stages_ms": {k: round(v, 3) for k, v in e2e_stage.items()}},
         "gpu_launches": int(launches),
+        "verify": verify_info,
         "clocks": clocks,
         # context only (vs_baseline stays null: BASELINE.json publishes no B200 number for this metric)
         "reference_published": {"value": 330.0, "unit": "s", "what": "the reference's own CPU prove of its README workload "

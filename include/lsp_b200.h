@@ -15,6 +15,7 @@
  *  - Host matrices are row-major (`RowMajorMatrix<Val>`, `trace/src/lib.rs:94-106`).
  *  - Every function returns 0 on success or a negative LSP_ERR_* code; nothing
  *    throws or aborts across the boundary.  `lsp_last_error` gives the text.
+ *    (lsp_verify_* additionally return a positive LSP_VERIFY_* reason for a rejected proof.)
  *  - One `lsp_ctx` per host thread; calls on a ctx are serialised on its stream.
  *  - There is no CPU fallback: without a CUDA device `lsp_ctx_create` fails.
  */
@@ -230,6 +231,38 @@ int lsp_prove_air(lsp_ctx* ctx, const lsp_fri_config* fri, const uint64_t* trace
 int lsp_prove_air_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp_mat* trace,
                       const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
                       const uint64_t publics[2][4], uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
+
+/* ---- `verify` (bin/src/main.rs:88-96) and `Mmcs::verify_batch` ---------------------- */
+/* Rejection reasons: POSITIVE return values of lsp_verify_* (0 = proof accepted, negative =
+ * LSP_ERR_*: the call itself failed).  They name the checks of p3_uni_stark::verify /
+ * TwoAdicFriPcs::verify in the order that verifier meets them; the first failing one is returned. */
+#define LSP_VERIFY_INVALID_PROOF_SHAPE 1      /* VerificationError::InvalidProofShape                                  */
+#define LSP_VERIFY_TRACE_OPENING 2            /* InvalidOpeningArgument(InputError(..)): trace round, Merkle root mismatch */
+#define LSP_VERIFY_QUOTIENT_OPENING 3         /* InvalidOpeningArgument(InputError(..)): quotient-chunk round           */
+#define LSP_VERIFY_COMMIT_PHASE_OPENING 4     /* InvalidOpeningArgument(CommitPhaseMmcsError(..))                       */
+#define LSP_VERIFY_FINAL_POLY_MISMATCH 5      /* InvalidOpeningArgument(FinalPolyMismatch)                              */
+#define LSP_VERIFY_INVALID_POW_WITNESS 6      /* InvalidOpeningArgument(InvalidPowWitness)                              */
+#define LSP_VERIFY_OOD_EVALUATION_MISMATCH 7  /* VerificationError::OodEvaluationMismatch                               */
+#define LSP_VERIFY_ROOT_MISMATCH 8            /* lsp_merkle_verify_batch only: MerkleTreeError::RootMismatch            */
+
+/* `verify(&config, &air, &mut challenger, &proof, &publics)` on the device: replays the transcript,
+ * checks the proof of work, every query's Merkle openings and fold chain against the final polynomial,
+ * and the out-of-domain identity  sum_i zp_i(zeta) chunk_i(zeta) = constraints(zeta) / Z_H(zeta).
+ * `proof` is the flat array lsp_prove_* wrote (host memory); `log_n` is the proof's `degree_bits`,
+ * `width` the AIR width.  `device_ms_out` (optional) receives the CUDA-event time of the whole check,
+ * upload included.  A proof with zero commit-phase rounds (log_final_poly_len == log_n) is rejected
+ * with FINAL_POLY_MISMATCH, as the pinned verifier does (the reduced opening only enters inside a round). */
+int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t log_n, size_t width,
+                   const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
+                   const uint64_t publics[2][4], const uint64_t* proof, size_t proof_words, float* device_ms_out);
+int lsp_verify_permutation(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t log_n, size_t width,
+                           const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                           const uint64_t* proof, size_t proof_words, float* device_ms_out);
+/* `verify_batch(&commit, dims, index, &opened_values, &proof)` for matrices of one height 2^log_height:
+ * `row` = the opened rows back to back (what lsp_merkle_open_batch returned), `siblings` = log_height digests.
+ * Returns 0 when the recomputed root equals `root`, LSP_VERIFY_ROOT_MISMATCH otherwise. */
+int lsp_merkle_verify_batch(lsp_ctx* ctx, const uint64_t root[4], uint32_t log_height, size_t index,
+                            const uint64_t* row, size_t row_len, const uint64_t* siblings);
 
 /* ---- multi-GPU: one proof sharded by row ranges of the LDE ---------- */
 typedef struct lsp_comm lsp_comm;

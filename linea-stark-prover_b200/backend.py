@@ -273,6 +273,22 @@ class GpuMmcs:
             o += w
         return opened, from_mont_array(sib)[:log_h]
 
+    def verify_batch(self, commit: int, log_height: int, index: int, opened_values, proof) -> bool:
+        """`verify_batch(&commit, dims, index, &opened_values, &proof)`: True when the opening is consistent
+        with `commit` (the reference returns `Err(RootMismatch)` otherwise)."""
+        flat = [x for row in opened_values for x in row]
+        rows = to_mont_array(flat)
+        sib = to_mont_array(list(proof)) if log_height else np.zeros((1, 4), dtype=np.uint64)
+        if len(proof) != log_height:
+            raise BackendError("verify_batch: proof length != log2(height)")
+        root = to_mont_array([commit])
+        rc = self.ctx.lib.lsp_merkle_verify_batch(self.ctx.h, ffi.as_u64p(root), log_height, index, ffi.as_u64p(rows), len(flat),
+                                                  ffi.as_u64p(sib))
+        if rc == VERIFY_ROOT_MISMATCH:
+            return False
+        self.ctx.check(rc, "lsp_merkle_verify_batch")
+        return True
+
 
 # ---------------------------------------------------------------------------
 # AIR config + prove (bin/src/main.rs:58-86)
@@ -483,6 +499,57 @@ def prove(ctx: Context, fri: FriConfig, cfgs, trace, publics, timings=None):
         timings.update({k: float(v) for k, v in zip(STAGE_NAMES, tm)})
     del keep, width
     return Proof(out, log_n, w, log_q, fri)
+
+
+# LSP_VERIFY_* (include/lsp_b200.h): the reference verifier's rejection reasons, in the order it meets them
+VERIFY_REASONS = {
+    1: "InvalidProofShape",
+    2: "InvalidOpeningArgument(InputError(RootMismatch)) [trace]",
+    3: "InvalidOpeningArgument(InputError(RootMismatch)) [quotient chunks]",
+    4: "InvalidOpeningArgument(CommitPhaseMmcsError(RootMismatch))",
+    5: "InvalidOpeningArgument(FinalPolyMismatch)",
+    6: "InvalidOpeningArgument(InvalidPowWitness)",
+    7: "OodEvaluationMismatch",
+}
+VERIFY_ROOT_MISMATCH = 8
+
+
+class VerificationError(Exception):
+    """`p3_uni_stark::VerificationError`; `.code` is the LSP_VERIFY_* value."""
+
+    def __init__(self, code: int):
+        super().__init__(VERIFY_REASONS.get(code, f"code {code}"))
+        self.code = code
+
+
+def verify_code(ctx: Context, fri: FriConfig, cfgs, proof, publics, log_n=None, width=None, timing=None) -> int:
+    """The raw result of `lsp_verify_air`: 0 = accepted, otherwise the LSP_VERIFY_* reason.  `proof` is a
+    `Proof` or a flat uint64 word array (then `log_n` and `width` must be given)."""
+    cf = fri.c_struct()
+    larr, n_l, arr, n_p, keep = _c_air_cfgs(cfgs)
+    pub = to_mont_array(publics)
+    assert pub.shape == (2, 4)
+    if isinstance(proof, Proof):
+        words, log_n, width = proof.words, proof.log_n, proof.width
+    else:
+        words = np.ascontiguousarray(proof, dtype=np.uint64).reshape(-1)
+    ms = np.zeros(1, dtype=np.float32)
+    rc = ctx.lib.lsp_verify_air(ctx.h, C.byref(cf), log_n, width, larr, n_l, arr, n_p, ffi.as_u64p(pub), ffi.as_u64p(words),
+                                words.size, ms.ctypes.data_as(ffi.f32p))
+    del keep
+    if rc < 0:
+        ctx.check(rc, "lsp_verify_air")
+    if timing is not None:
+        timing["device_ms"] = float(ms[0])
+    return int(rc)
+
+
+def verify(ctx: Context, fri: FriConfig, cfgs, proof, publics, log_n=None, width=None, timing=None) -> None:
+    """`verify(&config, &air, &mut challenger, &proof, &publics)` (bin/src/main.rs:88-96) on the device.
+    Returns None when the proof is accepted, raises `VerificationError` otherwise."""
+    rc = verify_code(ctx, fri, cfgs, proof, publics, log_n, width, timing)
+    if rc:
+        raise VerificationError(rc)
 
 
 def quotient_permutation(ctx: Context, lde: Mat, log_n: int, log_q: int, cfgs, publics, alpha) -> Mat:

@@ -129,6 +129,54 @@ __global__ void __launch_bounds__(32) k_ch_apply_witness(const __grid_constant__
     (void)ch_sample<D>(P, ch);  // ... then sample_bits(bits) consumes one sample
 }
 
+// The verifier's whole transcript in one launch (one warp): every challenge `verify` + `TwoAdicFriPcs::verify`
+// draw, in their order.  Nothing here depends on the query data, so the
+// per-query kernels can all start from its outputs.
+template <int D>
+__global__ void __launch_bounds__(32) k_verify_transcript(const __grid_constant__ P2Params P, DevChallenger* ch,
+                                                          const __grid_constant__ VerifyTranscriptArgs A) {
+    const bool lead = threadIdx.x == 0;
+    auto observe = [&](const Fr* v, int n) {
+        if (lead)
+            for (int i = 0; i < n; i++) ch_observe(ch, fr_load(v + i));
+        __syncwarp();
+    };
+    auto sample_to = [&](Fr* out) {
+        Fr v = ch_sample<D>(P, ch);
+        if (lead) fr_store(out, v);
+    };
+    auto sample_bits = [&](int bits) {
+        Fr c = fr_from_mont(ch_sample<D>(P, ch));
+        return bits >= 32 ? c.l[0] : (c.l[0] & ((1u << bits) - 1u));
+    };
+    if (lead) {
+        ch->n_input = 0;
+        ch->overflow = 0;
+        Fr ln = fr_zero();
+        ln.l[0] = uint32_t(A.log_n);
+        ch_observe(ch, fr_mul(ln, fr_const(FR_R2)));      // observe(degree_bits)
+    }
+    __syncwarp();
+    observe(A.trace_commit, 1);
+    observe(A.publics, 2);
+    sample_to(A.scal + VT_ALPHA);
+    observe(A.quot_commit, 1);
+    sample_to(A.scal + VT_ZETA);
+    sample_to(A.scal + VT_ALPHA_FRI);                       // (fork-era order) batching challenge before the betas
+    for (int r = 0; r < A.n_rounds; r++) {
+        observe(A.fri_commits + r, 1);
+        sample_to(A.betas + r);
+    }
+    observe(A.final_poly, A.n_final);
+    observe(A.pow_witness, 1);                              // check_witness: observe, then sample_bits == 0
+    uint32_t pow_low = sample_bits(A.pow_bits);
+    if (lead) *A.pow_low = pow_low;
+    for (int q = 0; q < A.n_queries; q++) {
+        uint32_t i = sample_bits(A.log_l);
+        if (lead) A.idx[q] = i;
+    }
+}
+
 int challenger_init(lsp_ctx* ctx, DevChallenger* ch) {
     LSP_LAUNCH(ctx, k_ch_init, 1, 1, 0, ch);
     return LSP_OK;
@@ -143,6 +191,10 @@ int challenger_sample(lsp_ctx* ctx, DevChallenger* ch, Fr* out_dev) {
 }
 int challenger_sample_bits(lsp_ctx* ctx, DevChallenger* ch, int bits, int n, uint32_t* idx_out) {
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample_bits<D>, 1, 32, 0, ctx->p2, ch, bits, n, idx_out));
+    return LSP_OK;
+}
+int verify_transcript(lsp_ctx* ctx, DevChallenger* ch, const VerifyTranscriptArgs& A) {
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_verify_transcript<D>, 1, 32, 0, ctx->p2, ch, A));
     return LSP_OK;
 }
 int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out) {
@@ -426,80 +478,7 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
         Fr is_first = fr_mul(zh, fr_load_nc(A.inv_first + p));
         Fr is_last = fr_mul(zh, fr_load_nc(A.inv_last + p));
         Fr is_trans = fr_sub(x, w_n_inv);
-        Fr acc = fr_zero();
-        bool first_c = true;
-        // ---- eval_lookup (air/src/lib.rs:57-114), one pass per AirLookupConfig ----------------
-        for (int k = 0; k < A.cfg.n_lookups; k++) {
-            const uint32_t* r = A.cfg.lk + A.cfg.lk_off[k];
-            const uint32_t n_a = r[0], n_t = r[1], n_b = r[2];
-            const Fr* col_af = A.lde + size_t(r[3]) * A.lde_rows;
-            const Fr* col_ai = A.lde + size_t(r[4]) * A.lde_rows;
-            const Fr* col_chk = A.lde + size_t(r[5]) * A.lde_rows;
-            const uint32_t* a_ids = r + 6;
-            Fr a_l = fr_load_nc(A.lde + size_t(a_ids[0]) * A.lde_rows + p);        // :65-68
-            for (uint32_t j = 1; j < n_a; j++) a_l = fr_add(fr_mul(a_l, alpha_air), fr_load_nc(A.lde + size_t(a_ids[j]) * A.lde_rows + p));
-            a_l = fr_add(a_l, delta);                                               // :70
-            const Fr ai_l = fr_load_nc(col_ai + p), ai_n = fr_load_nc(col_ai + pn);
-            Fr c = fr_sub(fr_mul(a_l, ai_l), one);                                  // :73
-            acc = first_c ? c : fr_add(fr_mul(acc, alpha), c);
-            first_c = false;
-            Fr chk_l_expr = fr_mul(fr_load_nc(col_af + p), ai_l);                   // :75
-            Fr chk_n_expr = fr_mul(fr_load_nc(col_af + pn), ai_n);                  // :76
-            const uint32_t* t_rec = a_ids + n_a;
-            for (uint32_t t = 0; t < n_t; t++, t_rec += 3 + n_b) {
-                const Fr* col_bf = A.lde + size_t(t_rec[0]) * A.lde_rows;
-                const Fr* col_bi = A.lde + size_t(t_rec[1]) * A.lde_rows;
-                const Fr* col_oc = A.lde + size_t(t_rec[2]) * A.lde_rows;
-                const uint32_t* b_ids = t_rec + 3;
-                Fr b_l = fr_load_nc(A.lde + size_t(b_ids[0]) * A.lde_rows + p);     // :79-82
-                for (uint32_t j = 1; j < n_b; j++) b_l = fr_add(fr_mul(b_l, alpha_air), fr_load_nc(A.lde + size_t(b_ids[j]) * A.lde_rows + p));
-                b_l = fr_add(b_l, delta);                                           // :84
-                const Fr bi_l = fr_load_nc(col_bi + p), bi_n = fr_load_nc(col_bi + pn);
-                c = fr_sub(fr_mul(b_l, bi_l), one);                                 // :85-88
-                acc = fr_add(fr_mul(acc, alpha), c);
-                chk_l_expr = fr_sub(chk_l_expr, fr_mul(fr_mul(fr_load_nc(col_bf + p), fr_load_nc(col_oc + p)), bi_l));     // :90-92
-                chk_n_expr = fr_sub(chk_n_expr, fr_mul(fr_mul(fr_load_nc(col_bf + pn), fr_load_nc(col_oc + pn)), bi_n));   // :94-96
-            }
-            const Fr chk_l = fr_load_nc(col_chk + p), chk_n = fr_load_nc(col_chk + pn);
-            acc = fr_add(fr_mul(acc, alpha), fr_mul(is_first, fr_sub(chk_l, chk_l_expr)));                  // :100-102
-            acc = fr_add(fr_mul(acc, alpha), fr_mul(is_trans, fr_sub(fr_sub(chk_n, chk_l), chk_n_expr)));  // :105-107
-            acc = fr_add(fr_mul(acc, alpha), fr_mul(is_last, chk_l));                                       // :110-112
-        }
-        // ---- eval_permutation (air/src/lib.rs:116-167) -----------------------------------------
-        for (int k = 0; k < A.cfg.n_cfgs; k++) {
-            const uint32_t nc = A.cfg.n_cols[k];
-            const uint32_t* a_ids = A.cfg.ids + A.cfg.ids_off[k];
-            const uint32_t* b_ids = a_ids + nc;
-            const Fr* col_inv = A.lde + size_t(A.cfg.b_inverse_id[k]) * A.lde_rows;
-            const Fr* col_chk = A.lde + size_t(A.cfg.check_id[k]) * A.lde_rows;
-            // Horner combinations (air/src/lib.rs:129-137,150-153): comb = comb*alpha + col
-            Fr a_l = fr_load_nc(A.lde + size_t(a_ids[0]) * A.lde_rows + p);
-            Fr b_l = fr_load_nc(A.lde + size_t(b_ids[0]) * A.lde_rows + p);
-            Fr a_n = fr_load_nc(A.lde + size_t(a_ids[0]) * A.lde_rows + pn);
-            for (uint32_t j = 1; j < nc; j++) {
-                a_l = fr_add(fr_mul(a_l, alpha_air), fr_load_nc(A.lde + size_t(a_ids[j]) * A.lde_rows + p));
-                b_l = fr_add(fr_mul(b_l, alpha_air), fr_load_nc(A.lde + size_t(b_ids[j]) * A.lde_rows + p));
-                a_n = fr_add(fr_mul(a_n, alpha_air), fr_load_nc(A.lde + size_t(a_ids[j]) * A.lde_rows + pn));
-            }
-            a_l = fr_add(a_l, delta);
-            b_l = fr_add(b_l, delta);
-            a_n = fr_add(a_n, delta);
-            Fr inv_l = fr_load_nc(col_inv + p), inv_n = fr_load_nc(col_inv + pn);
-            Fr chk_l = fr_load_nc(col_chk + p), chk_n = fr_load_nc(col_chk + pn);
-            // C0: b_ch * inv - 1                                  (:143)
-            Fr c0 = fr_sub(fr_mul(b_l, inv_l), one);
-            // C1: is_first * (check - a_ch * inv)                  (:146-148)
-            Fr c1 = fr_mul(is_first, fr_sub(chk_l, fr_mul(a_l, inv_l)));
-            // C2: is_transition * (check' - check * a_ch' * inv')  (:158-161)
-            Fr c2 = fr_mul(is_trans, fr_sub(chk_n, fr_mul(fr_mul(chk_l, a_n), inv_n)));
-            // C3: is_last * (check - 1)                            (:164-166)
-            Fr c3 = fr_mul(is_last, fr_sub(chk_l, one));
-            acc = first_c ? c0 : fr_add(fr_mul(acc, alpha), c0);
-            first_c = false;
-            acc = fr_add(fr_mul(acc, alpha), c1);
-            acc = fr_add(fr_mul(acc, alpha), c2);
-            acc = fr_add(fr_mul(acc, alpha), c3);
-        }
+        Fr acc = fold_air_constraints(A.cfg, A.lde, A.lde_rows, p, pn, alpha_air, delta, alpha, is_first, is_last, is_trans);
         Fr qv = fr_mul(acc, zh_inv);
         // split_evals: chunk c holds natural rows c, c+q, ...
         fr_store(A.chunks + (size_t(c) << A.log_n) + (i >> A.log_q), qv);

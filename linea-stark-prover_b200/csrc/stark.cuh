@@ -69,6 +69,102 @@ struct PermCfgDev {  // flattened LineaAIR config list in device memory: lookups
     const uint32_t* check_id;
 };
 
+// LineaAIR::eval folded by powers of the STARK challenge (ProverConstraintFolder / VerifierConstraintFolder,
+// acc = acc * alpha + constraint): lookups first, then permutations, as `oracle/air.py` orders them.
+// Row `p` is the local row, `pn` the next one; element (column c, row r) is lde[c * lde_rows + r].  The quotient
+// kernel calls it on LDE rows, the verifier on the opened values (lde_rows = 1, p = 0, pn = width).
+__device__ __forceinline__ Fr fold_air_constraints(const PermCfgDev& cfg, const Fr* __restrict__ lde, size_t lde_rows, size_t p,
+                                                   size_t pn, const Fr& alpha_air, const Fr& delta, const Fr& alpha,
+                                                   const Fr& is_first, const Fr& is_last, const Fr& is_trans) {
+    const Fr one = fr_one();
+    Fr acc = fr_zero();
+    bool first_c = true;
+    // ---- eval_lookup (air/src/lib.rs:57-114), one pass per AirLookupConfig ----------------
+    for (int k = 0; k < cfg.n_lookups; k++) {
+        const uint32_t* r = cfg.lk + cfg.lk_off[k];
+        const uint32_t n_a = r[0], n_t = r[1], n_b = r[2];
+        const Fr* col_af = lde + size_t(r[3]) * lde_rows;
+        const Fr* col_ai = lde + size_t(r[4]) * lde_rows;
+        const Fr* col_chk = lde + size_t(r[5]) * lde_rows;
+        const uint32_t* a_ids = r + 6;
+        Fr a_l = fr_load_nc(lde + size_t(a_ids[0]) * lde_rows + p);        // :65-68
+        for (uint32_t j = 1; j < n_a; j++) a_l = fr_add(fr_mul(a_l, alpha_air), fr_load_nc(lde + size_t(a_ids[j]) * lde_rows + p));
+        a_l = fr_add(a_l, delta);                                               // :70
+        const Fr ai_l = fr_load_nc(col_ai + p), ai_n = fr_load_nc(col_ai + pn);
+        Fr c = fr_sub(fr_mul(a_l, ai_l), one);                                  // :73
+        acc = first_c ? c : fr_add(fr_mul(acc, alpha), c);
+        first_c = false;
+        Fr chk_l_expr = fr_mul(fr_load_nc(col_af + p), ai_l);                   // :75
+        Fr chk_n_expr = fr_mul(fr_load_nc(col_af + pn), ai_n);                  // :76
+        const uint32_t* t_rec = a_ids + n_a;
+        for (uint32_t t = 0; t < n_t; t++, t_rec += 3 + n_b) {
+            const Fr* col_bf = lde + size_t(t_rec[0]) * lde_rows;
+            const Fr* col_bi = lde + size_t(t_rec[1]) * lde_rows;
+            const Fr* col_oc = lde + size_t(t_rec[2]) * lde_rows;
+            const uint32_t* b_ids = t_rec + 3;
+            Fr b_l = fr_load_nc(lde + size_t(b_ids[0]) * lde_rows + p);     // :79-82
+            for (uint32_t j = 1; j < n_b; j++) b_l = fr_add(fr_mul(b_l, alpha_air), fr_load_nc(lde + size_t(b_ids[j]) * lde_rows + p));
+            b_l = fr_add(b_l, delta);                                           // :84
+            const Fr bi_l = fr_load_nc(col_bi + p), bi_n = fr_load_nc(col_bi + pn);
+            c = fr_sub(fr_mul(b_l, bi_l), one);                                 // :85-88
+            acc = fr_add(fr_mul(acc, alpha), c);
+            chk_l_expr = fr_sub(chk_l_expr, fr_mul(fr_mul(fr_load_nc(col_bf + p), fr_load_nc(col_oc + p)), bi_l));     // :90-92
+            chk_n_expr = fr_sub(chk_n_expr, fr_mul(fr_mul(fr_load_nc(col_bf + pn), fr_load_nc(col_oc + pn)), bi_n));   // :94-96
+        }
+        const Fr chk_l = fr_load_nc(col_chk + p), chk_n = fr_load_nc(col_chk + pn);
+        acc = fr_add(fr_mul(acc, alpha), fr_mul(is_first, fr_sub(chk_l, chk_l_expr)));                  // :100-102
+        acc = fr_add(fr_mul(acc, alpha), fr_mul(is_trans, fr_sub(fr_sub(chk_n, chk_l), chk_n_expr)));  // :105-107
+        acc = fr_add(fr_mul(acc, alpha), fr_mul(is_last, chk_l));                                       // :110-112
+    }
+    // ---- eval_permutation (air/src/lib.rs:116-167) -----------------------------------------
+    for (int k = 0; k < cfg.n_cfgs; k++) {
+        const uint32_t nc = cfg.n_cols[k];
+        const uint32_t* a_ids = cfg.ids + cfg.ids_off[k];
+        const uint32_t* b_ids = a_ids + nc;
+        const Fr* col_inv = lde + size_t(cfg.b_inverse_id[k]) * lde_rows;
+        const Fr* col_chk = lde + size_t(cfg.check_id[k]) * lde_rows;
+        // Horner combinations (air/src/lib.rs:129-137,150-153): comb = comb*alpha + col
+        Fr a_l = fr_load_nc(lde + size_t(a_ids[0]) * lde_rows + p);
+        Fr b_l = fr_load_nc(lde + size_t(b_ids[0]) * lde_rows + p);
+        Fr a_n = fr_load_nc(lde + size_t(a_ids[0]) * lde_rows + pn);
+        for (uint32_t j = 1; j < nc; j++) {
+            a_l = fr_add(fr_mul(a_l, alpha_air), fr_load_nc(lde + size_t(a_ids[j]) * lde_rows + p));
+            b_l = fr_add(fr_mul(b_l, alpha_air), fr_load_nc(lde + size_t(b_ids[j]) * lde_rows + p));
+            a_n = fr_add(fr_mul(a_n, alpha_air), fr_load_nc(lde + size_t(a_ids[j]) * lde_rows + pn));
+        }
+        a_l = fr_add(a_l, delta);
+        b_l = fr_add(b_l, delta);
+        a_n = fr_add(a_n, delta);
+        Fr inv_l = fr_load_nc(col_inv + p), inv_n = fr_load_nc(col_inv + pn);
+        Fr chk_l = fr_load_nc(col_chk + p), chk_n = fr_load_nc(col_chk + pn);
+        // C0: b_ch * inv - 1                                  (:143)
+        Fr c0 = fr_sub(fr_mul(b_l, inv_l), one);
+        // C1: is_first * (check - a_ch * inv)                  (:146-148)
+        Fr c1 = fr_mul(is_first, fr_sub(chk_l, fr_mul(a_l, inv_l)));
+        // C2: is_transition * (check' - check * a_ch' * inv')  (:158-161)
+        Fr c2 = fr_mul(is_trans, fr_sub(chk_n, fr_mul(fr_mul(chk_l, a_n), inv_n)));
+        // C3: is_last * (check - 1)                            (:164-166)
+        Fr c3 = fr_mul(is_last, fr_sub(chk_l, one));
+        acc = first_c ? c0 : fr_add(fr_mul(acc, alpha), c0);
+        first_c = false;
+        acc = fr_add(fr_mul(acc, alpha), c1);
+        acc = fr_add(fr_mul(acc, alpha), c2);
+        acc = fr_add(fr_mul(acc, alpha), c3);
+    }
+    return acc;
+}
+
+// Everything the verifier's transcript reads and writes (device pointers; the proof regions point into the
+// uploaded proof).  scal receives [alpha, zeta, alpha_fri].
+enum { VT_ALPHA = 0, VT_ZETA = 1, VT_ALPHA_FRI = 2, VT_COUNT = 3 };
+struct VerifyTranscriptArgs {
+    int log_n, n_rounds, n_final, pow_bits, log_l, n_queries;
+    const Fr *trace_commit, *quot_commit, *publics, *fri_commits, *final_poly, *pow_witness;
+    Fr *scal, *betas;
+    uint32_t *pow_low, *idx;
+};
+int verify_transcript(lsp_ctx* ctx, DevChallenger* ch, const VerifyTranscriptArgs& A);
+
 int challenger_init(lsp_ctx* ctx, DevChallenger* ch);
 int challenger_observe_dev(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals, int n);
 int challenger_observe_host(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals_host, int n);

@@ -102,6 +102,11 @@ SIGNATURES = {
                                 C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
     "lsp_prove_air_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(LookupAirCfg), C.c_int, C.POINTER(PermAirCfg), C.c_int,
                                     u64p, u64p, C.c_size_t, f32p]),
+    "lsp_verify_air": (C.c_int, [vp, C.POINTER(FriConfig), C.c_uint32, C.c_size_t, C.POINTER(LookupAirCfg), C.c_int,
+                                 C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
+    "lsp_verify_permutation": (C.c_int, [vp, C.POINTER(FriConfig), C.c_uint32, C.c_size_t, C.POINTER(PermAirCfg), C.c_int,
+                                         u64p, u64p, C.c_size_t, f32p]),
+    "lsp_merkle_verify_batch": (C.c_int, [vp, u64p, C.c_uint32, C.c_size_t, u64p, C.c_size_t, u64p]),
     "lsp_prove_permutation_sharded": (C.c_int, [vp, C.POINTER(FriConfig), u64p, C.c_size_t, C.c_size_t,
                                                 C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
     "lsp_prove_permutation_sharded_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(PermAirCfg), C.c_int, u64p, u64p,

@@ -8,8 +8,8 @@
 //                                                                                        lsp_permutation_trace_be, lsp_mat_hconcat
 //   Perm::new_from_rng(8, 22, rng), Hash, Compress, Mmcs, FriConfig, Pcs     :49-68   -> lsp_set_poseidon2, lsp_fri_config
 //   LineaAIR::new(cfgs); prove(..)                                           :76-86   -> lsp_prove_air_dev
-//   verify(..)                                                               :90-96   stays with the unchanged Plonky3
-//                                                                                     verifier: the proof is written to --out
+//   verify(..)                                                               :88-96   -> lsp_verify_air (the proof is also
+//                                                                                        written to --out for any other verifier)
 // This file includes only include/lsp_b200.h and the C++ standard library: it is the binding a host
 // written in a compiled language would use, and it cannot fall back to anything -- no device, no proof.
 //
@@ -229,10 +229,21 @@ int main(int argc, char** argv) {
     for (uint64_t w : proof)
         for (int b = 0; b < 8; b++) h = (h ^ ((w >> (8 * b)) & 0xff)) * 1099511628211ull;
     printf("proof: %zu field elements, fnv1a64 %016llx\n", words / 4, (unsigned long long)h);
+    // ---- verify (main.rs:88-96): a fresh transcript over the proof, on the device
+    printf("Verifying...\n");
+    float verify_ms = 0;
+    int verdict = lsp_verify_air(ctx, &fri, uint32_t(log_n), col, lcfg.data(), int(lcfg.size()), pcfg.data(), int(pcfg.size()), publics,
+                                 proof.data(), words, &verify_ms);
+    if (verdict < 0) CHECK(ctx, verdict);
+    printf("verify [ %.3f ms ]: %s\n", verify_ms, verdict == 0 ? "proof accepted" : "PROOF REJECTED");
+    if (verdict != 0) {
+        fprintf(stderr, "verification failed: LSP_VERIFY code %d\n", verdict);
+        return 2;
+    }
     if (!out_path.empty()) {
         std::ofstream f(out_path, std::ios::binary);
         f.write(reinterpret_cast<const char*>(proof.data()), std::streamsize(words * 8));
-        printf("proof written to %s (hand it to the unchanged Plonky3 verifier: layout in DESIGN.md section 7)\n", out_path.c_str());
+        printf("proof written to %s (layout in DESIGN.md section 7)\n", out_path.c_str());
     }
     lsp_mat_free(ctx, trace);
     for (lsp_mat* m : parts) lsp_mat_free(ctx, m);

@@ -1,0 +1,414 @@
+// Device verifier: `p3_uni_stark::verify` over `TwoAdicFriPcs::verify`, the call the reference's
+// `main` makes right after `prove` (bin/src/main.rs:88-96), plus `Mmcs::verify_batch`
+// (bin/src/config.rs:19-20) on its own.
+//
+// Verification is a few thousand permutations, so the shape is latency, not throughput:
+//   1. k_verify_transcript (stark.cu)  one warp replays the whole Fiat-Shamir transcript: alpha, zeta,
+//                                      the FRI batching challenge, every beta, the proof-of-work check
+//                                      and all query indices.  Nothing in it depends on query data.
+//   2. k_verify_fold                   one thread per query: index check, reduced opening at the queried
+//                                      point (two inversions), the fold chain through every round (the
+//                                      round points are a squaring chain, no inversion), final-polynomial
+//                                      check.  Writes the leaf pair of every commit-phase opening.
+//   3. k_verify_path_jobs + k_merkle_paths   one thread per (query, tree) Merkle path -- trace, quotient,
+//                                      one per FRI round: 33 x 21 independent paths at the baseline shape.
+//   4. k_verify_ood                    quotient recombination and the AIR constraints at zeta, through
+//                                      the same fold_air_constraints the quotient kernel uses.
+// The host then reads one small status block and reports the FIRST failing check in the
+// reference verifier's order, so a rejected proof yields the same reason as the CPU verifier.
+//
+// Proof layout: see prover.cu.  The stored per-query index is redundant (the verifier samples
+// it); a proof whose stored index differs is rejected as malformed.
+#include "../csrc/stark.cuh"
+
+using namespace lsp;
+
+namespace lsp {
+
+struct PathJob {
+    const Fr* row;    // leaf row, `width` elements
+    const Fr* sibs;   // log_h siblings, leaf level first
+    const Fr* root;
+    int* bad;         // set to 1 when the recomputed root differs
+    uint32_t index;
+    int width, log_h;
+};
+
+// MerkleTreeMmcs::verify_batch for one matrix: hash the row (PaddingFreeSponge, rate 2), then
+// compress with the siblings up to the root.  Sponge steps and tree levels share ONE inlined
+// permutation site.
+template <int D>
+__global__ void __launch_bounds__(32) k_merkle_paths(const __grid_constant__ P2Params P, const PathJob* __restrict__ jobs, int n_jobs) {
+    LSP_P2_SLOT_DECL(32);
+    const int t = blockIdx.x * 32 + threadIdx.x;
+    const bool live = t < n_jobs;
+    const PathJob J = jobs[live ? t : 0];
+    const int n_leaf = (J.width + 1) / 2, total = n_leaf + J.log_h;
+    Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
+#pragma unroll 1
+    for (int step = 0; step < total; step++) {
+        if (step < n_leaf) {
+            const int c = 2 * step;
+            s0 = fr_load(J.row + c);
+            if (c + 1 < J.width) s1 = fr_load(J.row + c + 1);  // odd tail: state[1] keeps its stale value
+        } else {
+            const int k = step - n_leaf;
+            const Fr sib = fr_load(J.sibs + k), node = s0;
+            const bool right = (J.index >> k) & 1u;
+            s0 = right ? sib : node;
+            s1 = right ? node : sib;
+            s2 = fr_zero();
+        }
+        p2_permute<D, 32>(P, s0, s1, s2, LSP_P2_SLOT(32));
+    }
+    if (live) {
+        const Fr root = fr_load(J.root);
+        bool same = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) same = same && (root.l[i] == s0.l[i]);
+        *J.bad = same ? 0 : 1;
+    }
+}
+
+struct VerifyArgs {
+    const Fr *proof, *p_local, *p_next, *p_chunks, *p_commits, *p_final, *p_queries;
+    const Fr *publics, *scal, *betas;
+    const uint32_t* idx;
+    int W, q, log_n, log_q, log_l, n_rounds, n_final, n_queries;
+    size_t per_query;
+    Fr* ev;        // n_queries x n_rounds x 2: leaf rows of the commit-phase openings
+    int* status;   // n_queries x (4 + n_rounds): [index, final poly, trace path, quotient path, round paths...]
+    int* ood_bad;
+    PermCfgDev cfg;
+};
+constexpr int ST_INDEX = 0, ST_FINAL = 1, ST_TRACE = 2, ST_QUOT = 3, ST_ROUND = 4;
+
+__device__ __forceinline__ bool fr_same(const Fr& a, const Fr& b) {
+    bool s = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s = s && (a.l[i] == b.l[i]);
+    return s;
+}
+
+// verify_query for one query: open_input's reduced opening, then the fold chain.
+__global__ void __launch_bounds__(32) k_verify_fold(const __grid_constant__ VerifyArgs A) {
+    const int qi = blockIdx.x * 32 + threadIdx.x;
+    if (qi >= A.n_queries) return;
+    const uint32_t index = A.idx[qi];
+    const Fr* in = A.p_queries + size_t(qi) * A.per_query;
+    int* st = A.status + size_t(qi) * (ST_ROUND + A.n_rounds);
+    {   // the stored index is a raw integer and must be the sampled one
+        const Fr stored = fr_load(in);
+        bool ok = stored.l[0] == index;
+#pragma unroll
+        for (int i = 1; i < 8; i++) ok = ok && stored.l[i] == 0;
+        st[ST_INDEX] = ok ? 0 : 1;
+    }
+    const Fr* trow = in + 1;
+    const Fr* qrow = in + 1 + A.W + A.log_l;
+    const Fr zeta = fr_load(A.scal + VT_ZETA), a = fr_load(A.scal + VT_ALPHA_FRI);
+    const Fr zeta_next = fr_mul(zeta, fr_two_adic_generator(A.log_n));
+    // s = w_L^bitrev(index): the queried point is x = g * s
+    const Fr wl = fr_two_adic_generator(A.log_l);
+    const uint32_t e = bitrev32(index, A.log_l);
+    Fr s = fr_pow_u32(wl, e);
+    Fr s_inv = fr_pow_u32(wl, uint32_t(((size_t(1) << A.log_l) - e) & ((size_t(1) << A.log_l) - 1)));
+    const Fr x = fr_mul(fr_const(FR_GEN), s);
+    const Fr ix0 = fr_inv(fr_sub(x, zeta)), ix1 = fr_inv(fr_sub(x, zeta_next));
+    Fr ap = fr_one(), ro = fr_zero();
+    for (int c = 0; c < A.W; c++) {
+        ro = fr_add(ro, fr_mul(ap, fr_mul(fr_sub(fr_load(trow + c), fr_load(A.p_local + c)), ix0)));
+        ap = fr_mul(ap, a);
+    }
+    for (int c = 0; c < A.W; c++) {
+        ro = fr_add(ro, fr_mul(ap, fr_mul(fr_sub(fr_load(trow + c), fr_load(A.p_next + c)), ix1)));
+        ap = fr_mul(ap, a);
+    }
+    for (int c = 0; c < A.q; c++) {
+        ro = fr_add(ro, fr_mul(ap, fr_mul(fr_sub(fr_load(qrow + c), fr_load(A.p_chunks + c)), ix0)));
+        ap = fr_mul(ap, a);
+    }
+    // Fold chain.  In round r the element `di` of the round's domain sits at the point s_r (s_0 = s,
+    // s_{r+1} = s_r^2); the pair's even member is x0 = +-s_r, and 1/(x1 - x0) = -(1/2) / x0.
+    const Fr neg_half = fr_neg(fr_const(FR_HALF));
+    Fr folded = fr_zero();
+    uint32_t di = index;
+    size_t o = size_t(1) + A.W + A.log_l + A.q + A.log_l;
+    Fr* ev = A.ev + size_t(qi) * A.n_rounds * 2;
+    for (int r = 0; r < A.n_rounds; r++) {
+        if (r == 0) folded = fr_add(folded, ro);   // the only reduced opening on this path enters at the top height
+        const Fr sib = fr_load(in + o);
+        const bool odd = di & 1u;
+        const Fr ev0 = odd ? sib : folded, ev1 = odd ? folded : sib;
+        fr_store(ev + 2 * r, ev0);
+        fr_store(ev + 2 * r + 1, ev1);
+        const Fr x0 = odd ? fr_neg(s) : s, x0_inv = odd ? fr_neg(s_inv) : s_inv;
+        const Fr beta = fr_load(A.betas + r);
+        folded = fr_add(ev0, fr_mul(fr_mul(fr_sub(beta, x0), fr_sub(ev1, ev0)), fr_mul(neg_half, x0_inv)));
+        di >>= 1;
+        s = fr_sqr(s);
+        s_inv = fr_sqr(s_inv);
+        o += size_t(A.log_l - r);  // sibling value + (log_l - 1 - r) digests
+    }
+    // final polynomial at the remaining point (s after n_rounds squarings)
+    Fr acc = fr_zero(), xp = fr_one();
+    for (int j = 0; j < A.n_final; j++) {
+        acc = fr_add(acc, fr_mul(fr_load(A.p_final + j), xp));
+        xp = fr_mul(xp, s);
+    }
+    st[ST_FINAL] = fr_same(acc, folded) ? 0 : 1;
+}
+
+// One job per (query, tree): trace, quotient, then one per commit-phase round.
+__global__ void k_verify_path_jobs(const __grid_constant__ VerifyArgs A, PathJob* __restrict__ jobs) {
+    const int per = 2 + A.n_rounds;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.n_queries * per) return;
+    const int qi = t / per, path = t - qi * per;
+    const uint32_t index = A.idx[qi];
+    const Fr* in = A.p_queries + size_t(qi) * A.per_query;
+    int* st = A.status + size_t(qi) * (ST_ROUND + A.n_rounds);
+    PathJob J;
+    if (path == 0) {
+        J.row = in + 1;
+        J.width = A.W;
+        J.sibs = in + 1 + A.W;
+        J.log_h = A.log_l;
+        J.index = index;
+        J.root = A.proof;
+        J.bad = st + ST_TRACE;
+    } else if (path == 1) {
+        J.row = in + 1 + A.W + A.log_l;
+        J.width = A.q;
+        J.sibs = J.row + A.q;
+        J.log_h = A.log_l;
+        J.index = index;
+        J.root = A.proof + 1;
+        J.bad = st + ST_QUOT;
+    } else {
+        const int r = path - 2;
+        size_t o = size_t(1) + A.W + A.log_l + A.q + A.log_l + size_t(r) * A.log_l - size_t(r) * (r - 1) / 2;
+        J.row = A.ev + (size_t(qi) * A.n_rounds + r) * 2;
+        J.width = 2;
+        J.sibs = in + o + 1;
+        J.log_h = A.log_l - 1 - r;
+        J.index = index >> (r + 1);
+        J.root = A.p_commits + r;
+        J.bad = st + ST_ROUND + r;
+    }
+    jobs[t] = J;
+}
+
+// Out-of-domain check: sum_i zp_i(zeta) * chunk_i(zeta) == folded_constraints(zeta) / Z_H(zeta).
+// Threads (i, j), i != j, compute the factors of zp_i; thread 0 finishes.
+__global__ void __launch_bounds__(64) k_verify_ood(const __grid_constant__ VerifyArgs A) {
+    __shared__ Fr factor[64];
+    const int t = threadIdx.x, q = A.q, i = t / q, j = t - i * q;
+    const Fr zeta = fr_load(A.scal + VT_ZETA);
+    const Fr one = fr_one();
+    if (t < q * q && i != j) {
+        const Fr wnq = fr_two_adic_generator(A.log_n + A.log_q);
+        const Fr g = fr_const(FR_GEN);
+        const Fr shift_i = fr_mul(g, fr_pow_u32(wnq, uint32_t(i))), shift_j = fr_mul(g, fr_pow_u32(wnq, uint32_t(j)));
+        const Fr sj_inv = fr_inv(shift_j);
+        Fr a = fr_mul(zeta, sj_inv), b = fr_mul(shift_i, sj_inv);
+        for (int k = 0; k < A.log_n; k++) {
+            a = fr_sqr(a);
+            b = fr_sqr(b);
+        }
+        factor[t] = fr_mul(fr_sub(a, one), fr_inv(fr_sub(b, one)));
+    }
+    __syncthreads();
+    if (t != 0) return;
+    Fr quotient = fr_zero();
+    for (int ii = 0; ii < q; ii++) {
+        Fr zp = one;
+        for (int jj = 0; jj < q; jj++)
+            if (jj != ii) zp = fr_mul(zp, factor[ii * q + jj]);
+        quotient = fr_add(quotient, fr_mul(zp, fr_load(A.p_chunks + ii)));
+    }
+    Fr zn = zeta;
+    for (int k = 0; k < A.log_n; k++) zn = fr_sqr(zn);
+    const Fr z_h = fr_sub(zn, one);
+    const Fr wn_inv = fr_pow_u32(fr_two_adic_generator(A.log_n), uint32_t((size_t(1) << A.log_n) - 1));
+    const Fr is_first = fr_mul(z_h, fr_inv(fr_sub(zeta, one)));
+    const Fr is_last = fr_mul(z_h, fr_inv(fr_sub(zeta, wn_inv)));
+    const Fr is_trans = fr_sub(zeta, wn_inv);
+    const Fr folded = fold_air_constraints(A.cfg, A.p_local, 1, 0, size_t(A.W), fr_load(A.publics), fr_load(A.publics + 1),
+                                           fr_load(A.scal + VT_ALPHA), is_first, is_last, is_trans);
+    *A.ood_bad = fr_same(fr_mul(folded, fr_inv(z_h)), quotient) ? 0 : 1;
+}
+
+}  // namespace lsp
+
+extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t log_n, size_t width, const lsp_lookup_air_cfg* lookups,
+                              int n_lookups, const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
+                              const uint64_t* proof_words_in, size_t proof_words, float* device_ms_out) {
+    if (!ctx || !fri || !publics || !proof_words_in || n_lookups < 0 || n_cfgs < 0 || n_lookups + n_cfgs <= 0) return LSP_ERR_PARAM;
+    if ((n_cfgs && !cfgs) || (n_lookups && !lookups)) return LSP_ERR_PARAM;
+    if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
+    const int log_q = lsp_air_log_quotient_degree(n_lookups, n_cfgs), q = 1 << log_q;
+    const int log_b = int(fri->log_blowup), log_l = int(log_n) + log_b;
+    if (log_l > 31 || log_l < 1) return set_err(ctx, LSP_ERR_PARAM, "LDE of 2^%d rows unsupported", log_l);
+    if (fri->log_final_poly_len > log_n) return set_err(ctx, LSP_ERR_PARAM, "log_final_poly_len exceeds log2 of the trace height");
+    if (fri->num_queries == 0 || fri->num_queries > 4096) return set_err(ctx, LSP_ERR_PARAM, "num_queries out of range");
+    const int n_rounds = int(log_n) - int(fri->log_final_poly_len), log_f = log_b + int(fri->log_final_poly_len);
+    if ((size_t(1) << log_f) + 8 > size_t(CH_CAP)) return set_err(ctx, LSP_ERR_PARAM, "final polynomial of 2^%d coefficients unsupported", log_f);
+    // the proof's shape is a function of the parameters: any other length is InvalidProofShape
+    if (proof_words != lsp_proof_words(log_n, uint32_t(width), uint32_t(log_q), fri)) return LSP_VERIFY_INVALID_PROOF_SHAPE;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int W = int(width), nq = int(fri->num_queries);
+    const size_t proof_elems = proof_words / 4;
+    Scratch S(ctx);
+    PermCfgDev cfg_dev;
+    void* cfg_blob = nullptr;
+    LSP_TRY(upload_air_cfgs(ctx, lookups, n_lookups, cfgs, n_cfgs, width, &cfg_dev, &cfg_blob));
+    S.ptrs.push_back(cfg_blob);
+
+    cudaEvent_t ev0, ev1;
+    cudaEventCreate(&ev0);
+    cudaEventCreate(&ev1);
+    struct EvGuard {
+        cudaEvent_t a, b;
+        ~EvGuard() {
+            cudaEventDestroy(a);
+            cudaEventDestroy(b);
+        }
+    } ev_guard{ev0, ev1};
+    cudaEventRecord(ev0, ctx->stream);
+
+    Fr *proof = nullptr, *sc = nullptr, *betas = nullptr, *evbuf = nullptr;
+    LSP_TRY(S.get((void**)&proof, proof_elems * 32));
+    LSP_TRY(S.get((void**)&sc, (VT_COUNT + 2) * 32));
+    LSP_TRY(S.get((void**)&betas, size_t(n_rounds ? n_rounds : 1) * 32));
+    LSP_TRY(S.get((void**)&evbuf, size_t(nq) * (n_rounds ? n_rounds : 1) * 2 * 32));
+    const size_t st_per = size_t(ST_ROUND + n_rounds);
+    const size_t n_status = 2 + size_t(nq) * st_per;  // [pow_low, ood_bad, per-query blocks]
+    if ((n_status + 1) * 4 > ctx->pinned_bytes) return set_err(ctx, LSP_ERR_PARAM, "too many queries x rounds for the status block");
+    int* status = nullptr;
+    uint32_t* idx = nullptr;
+    DevChallenger* ch = nullptr;
+    PathJob* jobs = nullptr;
+    const int n_jobs = nq * (2 + n_rounds);
+    LSP_TRY(S.get((void**)&status, (n_status + 1) * 4));
+    LSP_TRY(S.get((void**)&idx, size_t(nq) * 4));
+    LSP_TRY(S.get((void**)&ch, sizeof(DevChallenger)));
+    LSP_TRY(S.get((void**)&jobs, size_t(n_jobs) * sizeof(PathJob)));
+    LSP_CUDA(ctx, cudaMemcpyAsync(proof, proof_words_in, proof_elems * 32, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaMemcpyAsync(sc + VT_COUNT, publics, 64, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaMemsetAsync(status, 0xff, (n_status + 1) * 4, ctx->stream));  // anything left unwritten reads as a failure
+
+    VerifyArgs A;
+    A.proof = proof;
+    A.p_local = proof + 2;
+    A.p_next = A.p_local + W;
+    A.p_chunks = A.p_next + W;
+    A.p_commits = A.p_chunks + q;
+    A.p_final = A.p_commits + n_rounds;
+    const Fr* p_pow = A.p_final + (size_t(1) << log_f);
+    A.p_queries = p_pow + 1;
+    A.publics = sc + VT_COUNT;
+    A.scal = sc;
+    A.betas = betas;
+    A.idx = idx;
+    A.W = W;
+    A.q = q;
+    A.log_n = int(log_n);
+    A.log_q = log_q;
+    A.log_l = log_l;
+    A.n_rounds = n_rounds;
+    A.n_final = 1 << log_f;
+    A.n_queries = nq;
+    A.per_query = (proof_elems - size_t(A.p_queries - proof)) / size_t(nq);
+    A.ev = evbuf;
+    A.status = status + 2;
+    A.ood_bad = status + 1;
+    A.cfg = cfg_dev;
+
+    ctx->phase = "verify";
+    VerifyTranscriptArgs T;
+    T.log_n = int(log_n);
+    T.n_rounds = n_rounds;
+    T.n_final = A.n_final;
+    T.pow_bits = int(fri->proof_of_work_bits);
+    T.log_l = log_l;
+    T.n_queries = nq;
+    T.trace_commit = proof;
+    T.quot_commit = proof + 1;
+    T.publics = A.publics;
+    T.fri_commits = A.p_commits;
+    T.final_poly = A.p_final;
+    T.pow_witness = p_pow;
+    T.scal = sc;
+    T.betas = betas;
+    T.pow_low = reinterpret_cast<uint32_t*>(status);
+    T.idx = idx;
+    LSP_TRY(verify_transcript(ctx, ch, T));
+    LSP_LAUNCH(ctx, k_verify_fold, unsigned((nq + 31) / 32), 32, 0, A);
+    LSP_LAUNCH(ctx, k_verify_path_jobs, unsigned((n_jobs + 127) / 128), 128, 0, A, jobs);
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_merkle_paths<D>, unsigned((n_jobs + 31) / 32), 32, 0, ctx->p2, (const PathJob*)jobs, n_jobs));
+    LSP_LAUNCH(ctx, k_verify_ood, 1, 64, 0, A);
+    LSP_CUDA(ctx, cudaMemcpyAsync(status + n_status, &ch->overflow, 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, status, (n_status + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ev1, ctx->stream);
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->phase = "";
+    if (device_ms_out) cudaEventElapsedTime(device_ms_out, ev0, ev1);
+    const int* h = static_cast<const int*>(ctx->pinned);
+    if (h[n_status]) return set_err(ctx, LSP_ERR_STATE, "challenger input buffer overflow");
+    // first failing check, in the order the reference verifier meets them
+    if (h[0] != 0) return LSP_VERIFY_INVALID_POW_WITNESS;
+    for (int qi = 0; qi < nq; qi++) {
+        const int* st = h + 2 + size_t(qi) * st_per;
+        if (st[ST_INDEX]) return LSP_VERIFY_INVALID_PROOF_SHAPE;
+        if (st[ST_TRACE]) return LSP_VERIFY_TRACE_OPENING;
+        if (st[ST_QUOT]) return LSP_VERIFY_QUOTIENT_OPENING;
+        for (int r = 0; r < n_rounds; r++)
+            if (st[ST_ROUND + r]) return LSP_VERIFY_COMMIT_PHASE_OPENING;
+        if (st[ST_FINAL]) return LSP_VERIFY_FINAL_POLY_MISMATCH;
+    }
+    if (h[1]) return LSP_VERIFY_OOD_EVALUATION_MISMATCH;
+    return LSP_OK;
+}
+
+extern "C" int lsp_verify_permutation(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t log_n, size_t width, const lsp_perm_air_cfg* cfgs,
+                                      int n_cfgs, const uint64_t publics[2][4], const uint64_t* proof_words_in, size_t proof_words,
+                                      float* device_ms_out) {
+    if (!cfgs || n_cfgs <= 0) return LSP_ERR_PARAM;
+    return lsp_verify_air(ctx, fri, log_n, width, nullptr, 0, cfgs, n_cfgs, publics, proof_words_in, proof_words, device_ms_out);
+}
+
+// `Mmcs::verify_batch(&commit, &[Dimensions], index, &opened_values, &proof)` for matrices of one height
+// (the only case on the reference's path): `row` = the opened rows back to back, as lsp_merkle_open_batch returns them.
+extern "C" int lsp_merkle_verify_batch(lsp_ctx* ctx, const uint64_t root[4], uint32_t log_height, size_t index, const uint64_t* row,
+                                       size_t row_len, const uint64_t* siblings) {
+    if (!ctx || !root || !row || row_len == 0 || row_len > (1u << 20) || log_height > 31 || (log_height && !siblings)) return LSP_ERR_PARAM;
+    if (index >> log_height) return LSP_ERR_PARAM;
+    if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch S(ctx);
+    Fr* buf = nullptr;
+    const size_t n_elems = 1 + row_len + log_height;
+    LSP_TRY(S.get((void**)&buf, n_elems * 32));
+    PathJob* job = nullptr;
+    LSP_TRY(S.get((void**)&job, sizeof(PathJob)));
+    int* bad = nullptr;
+    LSP_TRY(S.get((void**)&bad, 4));
+    LSP_CUDA(ctx, cudaMemcpyAsync(buf, root, 32, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaMemcpyAsync(buf + 1, row, row_len * 32, cudaMemcpyHostToDevice, ctx->stream));
+    if (log_height) LSP_CUDA(ctx, cudaMemcpyAsync(buf + 1 + row_len, siblings, size_t(log_height) * 32, cudaMemcpyHostToDevice, ctx->stream));
+    PathJob J;
+    J.row = buf + 1;
+    J.sibs = buf + 1 + row_len;
+    J.root = buf;
+    J.bad = bad;
+    J.index = uint32_t(index);
+    J.width = int(row_len);
+    J.log_h = int(log_height);
+    LSP_CUDA(ctx, cudaMemcpyAsync(job, &J, sizeof(J), cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaMemsetAsync(bad, 0xff, 4, ctx->stream));
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_merkle_paths<D>, 1, 32, 0, ctx->p2, (const PathJob*)job, 1));
+    LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return *static_cast<const int*>(ctx->pinned) ? LSP_VERIFY_ROOT_MISMATCH : LSP_OK;
+}

@@ -613,7 +613,7 @@ int lsp_oracle_verify(const fri_cfg* fri, uint32_t log_n, size_t width, const ai
     for (uint32_t qi = 0; qi < fri->num_queries && !rc; qi++) {
         size_t index = (size_t)ch_sample_bits(ch, log_l);
         const fr* in = p_queries + (size_t)qi * per_query; size_t o = 0;
-        if (in[o].l[0] != index) { rc = 1; break; }
+        if (in[o].l[0] != index || in[o].l[1] || in[o].l[2] || in[o].l[3]) { rc = 1; break; }   /* the stored index is a raw integer */
         o++;
         const fr* trow = in + o; o += W; const fr* tsib = in + o; o += log_l;
         const fr* qrow = in + o; o += q; const fr* qsib = in + o; o += log_l;

@@ -21,10 +21,15 @@ def run_smoke(log_n: int = 6, c: int = 3):
     oproof = OS.prove(p, fri, cfgs, trace, [alpha, delta], dbg)
     gcfgs = [pkg.AirPermutationConfig(x.a_columns_ids, x.b_columns_ids, x.b_inverse_id, x.check_id) for x in cfgs]
     launches0 = ctx.kernel_launches()
-    gd, idx = pkg.prove(ctx, pkg.FriConfig(), gcfgs, trace, [alpha, delta]).to_dict()
+    gproof = pkg.prove(ctx, pkg.FriConfig(), gcfgs, trace, [alpha, delta])
+    gd, idx = gproof.to_dict()
     assert ctx.kernel_launches() > launches0, "no CUDA kernels were launched"
     assert gd == oproof and idx == dbg["query_indices"], "GPU proof differs from the oracle's"
     OS.verify(p, fri, cfgs, gd, [alpha, delta])
+    pkg.verify(ctx, pkg.FriConfig(), gcfgs, gproof, [alpha, delta])      # the device verifier agrees
+    bad = gproof.words.copy()
+    bad[4 * 2] ^= 1
+    assert pkg.verify_code(ctx, pkg.FriConfig(), gcfgs, bad, [alpha, delta], log_n, gproof.width) != 0
     assert OA.check_constraints(cfgs, trace, [alpha, delta])
     ctx.close()
     print(f"smoke ok: 2^{log_n}-row permutation AIR proved on cuda:0, bit-exact with the oracle, verifier accepts")

@@ -214,4 +214,8 @@ def test_lookup_air_at_2p13_rows_matches_c_port(pkg, gctx, p2params):
     assert np.array_equal(cport.prove_limbs(ofri, limbs, n, w, cfgs, pub), gproof.words)
     bad = gproof.words.copy()
     bad[4 * (2 + cfgs[0].occurrences_id[0])] ^= 1
-    assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, bad) != 0
+    why = cport.verify_limbs(ofri, log_n, w, cfgs, pub, bad)
+    assert why != 0
+    # the device verifier: same verdicts, same reason
+    pkg.verify(gctx, pkg.FriConfig(**fri), _gpu_cfgs(pkg, cfgs), gproof, [alpha, delta])
+    assert pkg.verify_code(gctx, pkg.FriConfig(**fri), _gpu_cfgs(pkg, cfgs), bad, [alpha, delta], log_n, w) == why

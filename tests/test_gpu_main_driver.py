@@ -39,6 +39,7 @@ def test_driver_proves_cbor_files_like_main(pkg, tmp_path):
                         str(seed), "--queries", "9", "--out", str(out)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Proving..." in r.stdout and "commit to trace data" in r.stdout
+    assert "Verifying..." in r.stdout and "proof accepted" in r.stdout          # main.rs:88-96
     words = np.frombuffer(out.read_bytes(), dtype=np.uint64)
     # the same proof through the Python mirror, and the oracle accepts it
     p = Poseidon2Params(sbox_d=5, rounds_f=8, rounds_p=22, ext_initial=[consts[3 * i:3 * i + 3] for i in range(4)],

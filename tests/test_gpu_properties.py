@@ -89,3 +89,39 @@ def test_witness_satisfies_constraints_on_sampled_rows_at_2p19(pkg, gctx):
                          OA.Fe(1 if i == 0 else 0), OA.Fe(0), OA.Fe(1))
         assert all(x.v == 0 for x in cs), i
     assert dev.rows(n - 1, 1)[0][-1] == 1
+
+
+def test_random_shapes_against_the_c_port(pkg, gctx, p2params):
+    """Differential sweep: 40 seeded random shapes (height 2..2^12, 1..6 columns, blowup 2..8, final-poly length 1..4,
+    0..5 proof-of-work bits, 1..40 queries): the GPU proof must equal the C port's word for word and verify."""
+    from oracle import cport
+    from oracle import stark as OS
+    cport.set_poseidon2(p2params)
+    rng = np.random.default_rng(2026)
+    done = 0
+    for trial in range(60):
+        log_n = int(rng.integers(1, 13))
+        c = int(rng.integers(1, 7))
+        log_blowup = int(rng.integers(1, 4))
+        log_final = int(rng.integers(0, min(3, log_n + 1)))
+        fri_kw = dict(log_blowup=log_blowup, log_final_poly_len=log_final, num_queries=int(rng.integers(1, 41)),
+                      proof_of_work_bits=int(rng.integers(0, 6)))
+        if log_blowup + log_final > 10:
+            continue
+        pub, tr, n, w = cport.gen_trace(int(rng.integers(1, 1 << 30)), c, log_n)
+        cfgs = [OA.AirPermutationConfig.standard(c)]
+        g = [pkg.AirPermutationConfig(x.a_columns_ids, x.b_columns_ids, x.b_inverse_id, x.check_id) for x in cfgs]
+        ofri = OS.FriConfig(**fri_kw)
+        cwords = cport.prove_limbs(ofri, tr, n, w, cfgs, pub)
+        gproof = pkg.prove(gctx, pkg.FriConfig(**fri_kw), g, (tr, n, w), pkg.from_mont_array(pub))
+        assert np.array_equal(cwords, gproof.words), (log_n, c, fri_kw)
+        # Zero commit-phase rounds (final polynomial as long as the trace): the prover side is well defined and must
+        # still match, but the restated verifier -- like the pinned Plonky3 one it follows, whose query loop only adds the
+        # reduced opening inside a folding round -- rejects such a proof (shape error, code 5). Keep that pinned.
+        want = 5 if log_final == log_n else 0
+        assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, gproof.words) == want, (log_n, c, fri_kw)
+        assert pkg.verify_code(gctx, pkg.FriConfig(**fri_kw), g, gproof, pkg.from_mont_array(pub)) == want, (log_n, c, fri_kw)
+        done += 1
+        if done == 40:
+            break
+    assert done >= 30

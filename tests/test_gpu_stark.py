@@ -170,9 +170,12 @@ def test_full_size_prove_verifies_and_matches_cpu_port(pkg):
     cfgs = [OA.AirPermutationConfig.standard(c)]
     gproof = pkg.prove(ctx, pkg.FriConfig(), _gpu_cfgs(pkg, cfgs), (tr, n, w), pkg.from_mont_array(pub))
     assert cport.verify_limbs(fri, log_n, w, cfgs, pub, gproof.words) == 0
+    pkg.verify(ctx, pkg.FriConfig(), _gpu_cfgs(pkg, cfgs), gproof, pkg.from_mont_array(pub))      # the device verifier accepts it too
     bad = gproof.words.copy()
     bad[4 * 5] ^= 1
-    assert cport.verify_limbs(fri, log_n, w, cfgs, pub, bad) != 0
+    why = cport.verify_limbs(fri, log_n, w, cfgs, pub, bad)
+    assert why != 0
+    assert pkg.verify_code(ctx, pkg.FriConfig(), _gpu_cfgs(pkg, cfgs), bad, pkg.from_mont_array(pub), log_n, w) == why
     cwords = cport.prove_limbs(fri, tr, n, w, cfgs, pub)
     assert np.array_equal(cwords, gproof.words)
     # the device-side witness generator reproduces the CPU port's trace from its a/b columns
@@ -210,9 +213,12 @@ def test_baseline_configs_verify(pkg, name, log_n, c, log_blowup):
     gproof = pkg.prove(ctx, pkg.FriConfig(**fri_kw), _gpu_cfgs(pkg, cfgs), dev, pkg.from_mont_array(pub))
     ofri = OS.FriConfig(**fri_kw)
     assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, gproof.words) == 0
+    pkg.verify(ctx, pkg.FriConfig(**fri_kw), _gpu_cfgs(pkg, cfgs), gproof, pkg.from_mont_array(pub))
     bad = gproof.words.copy()
     bad[4 * 3 + 1] ^= 1 << 7
-    assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, bad) != 0
+    why = cport.verify_limbs(ofri, log_n, w, cfgs, pub, bad)
+    assert why != 0
+    assert pkg.verify_code(ctx, pkg.FriConfig(**fri_kw), _gpu_cfgs(pkg, cfgs), bad, pkg.from_mont_array(pub), log_n, w) == why
     ctx.close()
 
 
