@@ -8,19 +8,88 @@
 // handled.  This file only parses: the 32-byte big-endian values are handed to the device as they
 // are, and `from_be_bytes_mod_order` + the Montgomery conversion (:95-118) run in a kernel
 // (lsp_permutation_trace_be, csrc/witness.cu) -- no field arithmetic happens on the host.
+//
+// Speed (the file is ~50 bytes of CBOR per element, 400 MB at 12 columns x 2^19
+// rows, so a naive reader costs far more than the prove it feeds).  The structure pass is a serial
+// scan -- element sizes vary, so a column's end is only known by walking it -- with a branch-light
+// fast path for serde's canonical `98 20 <32 x (b | 18 b)>` element, and it records where every
+// column starts; the decode pass then parses the columns on all host threads at once.
+#include <algorithm>
+#include <atomic>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/lsp_b200.h"
 
 namespace {
 
+// serde's canonical `[u8;32]`: array(32) head `98 20`, then 32 values, each one byte (< 24) or `18 b`.
+// Returns the position after the element, or nullptr when the bytes at p are anything else.
+inline const uint8_t* fast_elem(const uint8_t* p, const uint8_t* end, uint8_t* dst) {
+    if (end - p < 34 || p[0] != 0x98 || p[1] != 0x20) return nullptr;
+    const uint8_t* q = p + 2;
+    unsigned bad = 0;
+    if (end - p >= 66) {            // the longest element fits: no bounds checks inside
+        if (dst) {
+            for (int k = 0; k < 32; k++) {
+                const uint8_t b = q[0], wide = b == 0x18;
+                bad |= b > 0x18;
+                dst[k] = wide ? q[1] : b;
+                q += 1 + wide;
+            }
+        } else {
+            for (int k = 0; k < 32; k++) {
+                const uint8_t b = q[0];
+                bad |= b > 0x18;
+                q += 1 + (b == 0x18);
+            }
+        }
+        return bad ? nullptr : q;
+    }
+    for (int k = 0; k < 32; k++) {  // the last elements of the file
+        if (q >= end) return nullptr;
+        const uint8_t b = *q++;
+        if (b > 0x18) return nullptr;
+        uint8_t v = b;
+        if (b == 0x18) {
+            if (q >= end) return nullptr;
+            v = *q++;
+        }
+        if (dst) dst[k] = v;
+    }
+    return q;
+}
+
+// A stretch of back-to-back canonical elements found by the parallel structure pass.  The serial
+// structural walk jumps over it in one step and notes which vector it belongs to and at which row.
+struct Run {
+    size_t off, end, count;
+    size_t vec_off = 0, row0 = 0;   // filled by the walk: head offset of the owning vector, first row
+    bool placed = false;
+};
+
 struct Reader {
     const uint8_t* p;
     const uint8_t* end;
     bool ok = true;
+    const uint8_t* base = nullptr;   // start of the file, for the column offsets the structure pass records
+    std::vector<Run>* runs = nullptr;   // sorted by off; when set, walk_vector jumps over them
+    size_t run_hint = 0;                // runs before this index lie behind p
+    size_t loose = 0;                   // elements met outside any run while runs are set
+
+    // The run starting exactly at p, if any.
+    Run* run_here() {
+        if (!runs) return nullptr;
+        const size_t o = size_t(p - base);
+        while (run_hint < runs->size() && (*runs)[run_hint].off < o) run_hint++;
+        if (run_hint < runs->size() && (*runs)[run_hint].off == o) return &(*runs)[run_hint];
+        return nullptr;
+    }
 
     bool need(size_t n) {
         if (size_t(end - p) < n) ok = false;
@@ -90,6 +159,10 @@ struct Reader {
     }
     // One `[u8;32]`: array(32) of uints < 256, or bytes(32).  `dst` may be null (shape pass).
     bool elem32(uint8_t* dst) {
+        if (const uint8_t* q = fast_elem(p, end, dst)) {
+            p = q;
+            return true;
+        }
         uint64_t arg;
         bool indef;
         int m = head(arg, indef);
@@ -115,6 +188,7 @@ struct Reader {
 
 struct Shape {
     std::vector<size_t> a_rows, b_rows;  // rows per column
+    std::vector<size_t> a_off, b_off;    // byte offset of every column's array head
     std::string name;
     size_t height() const {
         size_t h = 0;
@@ -124,33 +198,212 @@ struct Shape {
     }
 };
 
-// Walks `a` or `b`: array(columns) of array(rows) of [u8;32].  With `out` set, column j's row i is
-// written at out + ((i * stride_cols) + col0 + j) * 32.
-bool walk_columns(Reader& r, std::vector<size_t>* rows_out, uint8_t* out, size_t stride_cols, size_t col0) {
+// array(rows) of [u8;32]; row i goes to out + (i*stride + col)*32 when out != null and i < max_rows.  Returns the length.
+size_t walk_vector(Reader& r, uint8_t* out, size_t stride, size_t col, size_t max_rows) {
+    const size_t head_off = r.base ? size_t(r.p - r.base) : 0;   // (structure pass) identifies this vector: offset of its array head
+    uint64_t nr;
+    bool ir;
+    if (r.head(nr, ir) != 4) {
+        r.ok = false;
+        return 0;
+    }
+    size_t i = 0;
+    while (r.ok && (ir ? !r.at_break() : i < nr)) {
+        if (Run* run = r.run_here()) {          // structure pass over a pre-scanned file: a whole run at once
+            if (!ir && i + run->count > nr) {   // the run reaches past this vector: not the regular layout
+                r.ok = false;
+                break;
+            }
+            run->vec_off = head_off;
+            run->row0 = i;
+            run->placed = true;
+            i += run->count;
+            r.p = r.base + run->end;
+            continue;
+        }
+        if (r.runs) r.loose++;
+        r.elem32(out && i < max_rows ? out + (i * stride + col) * 32 : nullptr);
+        i++;
+    }
+    if (r.ok && ir) r.skip_break();
+    return i;
+}
+
+size_t host_threads() {
+    size_t nt = std::thread::hardware_concurrency();
+    if (const char* e = getenv("LSP_CBOR_THREADS")) nt = size_t(atoi(e));
+    if (nt == 0) nt = 1;
+    return nt > 64 ? 64 : nt;
+}
+
+// body(k) for k < n on up to host_threads() threads (dynamic schedule).
+template <class F>
+void parallel_for(size_t n, F body) {
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= n) break;
+            body(k);
+        }
+    };
+    size_t nt = host_threads();
+    if (nt > n) nt = n;
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nt; t++) pool.emplace_back(work);
+    work();
+    for (auto& th : pool) th.join();
+}
+
+// Parallel structure pre-pass.  In a file written by serde every element starts with `98 20`, and that byte pair
+// cannot occur anywhere else (a payload byte 98 is always followed by a value head, never by 20), so a
+// thread dropped at an arbitrary offset can resynchronise on it.  Each thread walks from its first marker to the
+// next thread's, counting back-to-back canonical elements into runs and stepping over the structural tokens
+// between them (array / map heads, breaks, text keys); it must land exactly on the next thread's marker.  Anything
+// else -- another element encoding, a 32-row column (whose head is also `98 20`), a marker inside a string --
+// makes the file "irregular": the caller falls back to the serial pass, which is the authority on malformed input.
+bool prescan(const uint8_t* cbor, size_t len, std::vector<Run>& runs) {
+    const size_t nt = host_threads();
+    size_t min_len = size_t(4) << 20, chunk = size_t(1) << 18;   // below 4 MB the serial pass is quick enough
+    if (const char* e = getenv("LSP_CBOR_PRESCAN_MIN")) {         // tests: force the parallel path on small files
+        min_len = size_t(atoll(e));
+        chunk = 64;
+    }
+    if (nt < 2 || len < min_len || len < 2 * chunk) return false;
+    size_t n_chunks = len / chunk;
+    if (n_chunks > 4 * nt) n_chunks = 4 * nt;
+    const size_t npos = ~size_t(0);
+    std::vector<size_t> first(n_chunks, npos);
+    parallel_for(n_chunks, [&](size_t t) {
+        const size_t s0 = len * t / n_chunks, e0 = len * (t + 1) / n_chunks;
+        for (const uint8_t* q = cbor + s0; q < cbor + e0;) {
+            q = static_cast<const uint8_t*>(memchr(q, 0x98, size_t(cbor + e0 - q)));
+            if (!q) break;
+            if (q + 1 < cbor + len && q[1] == 0x20) {
+                first[t] = size_t(q - cbor);
+                break;
+            }
+            q++;
+        }
+    });
+    std::vector<size_t> bounds;
+    for (size_t f : first)
+        if (f != npos) bounds.push_back(f);
+    if (bounds.empty()) return false;
+    std::vector<std::vector<Run>> per(bounds.size());
+    std::atomic<bool> regular{true};
+    parallel_for(bounds.size(), [&](size_t k) {
+        const uint8_t* end = cbor + len;
+        const uint8_t* p = cbor + bounds[k];
+        const uint8_t* lim = k + 1 < bounds.size() ? cbor + bounds[k + 1] : end;
+        Run cur{0, 0, 0};
+        while (p < lim && regular.load(std::memory_order_relaxed)) {
+            if (const uint8_t* q = fast_elem(p, end, nullptr)) {
+                if (cur.count == 0) cur.off = size_t(p - cbor);
+                cur.count++;
+                cur.end = size_t(q - cbor);
+                p = q;
+                continue;
+            }
+            if (cur.count) {
+                per[k].push_back(cur);
+                cur = Run{0, 0, 0};
+            }
+            Reader r{p, end};
+            uint64_t arg;
+            bool indef;
+            const int m = r.head(arg, indef);
+            bool fine = r.ok;
+            if (fine && m == 4) fine = indef || arg != 32;          // array(32): an element in another form, or a 32-row column
+            else if (fine && m == 3 && !indef) {                    // a map key or the name
+                fine = r.need(arg);
+                if (fine) r.p += arg;
+            } else if (fine) fine = m == 5 || (m == 7 && indef);    // map head, break
+            if (!fine) {
+                regular = false;
+                return;
+            }
+            p = r.p;
+        }
+        if (p != lim) regular = false;
+        if (cur.count) per[k].push_back(cur);
+    });
+    if (getenv("LSP_CBOR_DEBUG")) fprintf(stderr, "prescan: %zu chunks, %zu bounds, regular=%d\n", n_chunks, bounds.size(), int(regular.load()));
+    if (!regular) return false;
+    runs.clear();
+    for (auto& v : per) runs.insert(runs.end(), v.begin(), v.end());
+    return !runs.empty();
+}
+
+// One vector of the file (found by the structure pass) and the output column it fills.
+struct VecJob {
+    size_t off, col;
+};
+
+// Decode pass: every vector is parsed independently from its recorded offset, on all host threads.
+bool decode_jobs(const uint8_t* cbor, size_t len, const std::vector<VecJob>& jobs, uint8_t* out, size_t stride, size_t max_rows) {
+    std::atomic<bool> ok{true};
+    parallel_for(jobs.size(), [&](size_t k) {
+        Reader r{cbor + jobs[k].off, cbor + len};
+        walk_vector(r, out, stride, jobs[k].col, max_rows);
+        if (!r.ok) ok = false;
+    });
+    return ok;
+}
+
+// Decode pass over a pre-scanned file: one task per run (a slice of one column), so the work spreads over all
+// threads whatever the number of columns.  Runs of vectors that are not in `jobs` (filters of absent tables) are dropped.
+bool decode_runs(const uint8_t* cbor, size_t len, const std::vector<Run>& runs, const std::vector<VecJob>& jobs, uint8_t* out,
+                 size_t stride, size_t max_rows) {
+    std::vector<VecJob> by_off(jobs);
+    std::sort(by_off.begin(), by_off.end(), [](const VecJob& a, const VecJob& b) { return a.off < b.off; });
+    std::atomic<bool> ok{true};
+    parallel_for(runs.size(), [&](size_t k) {
+        const Run& run = runs[k];
+        auto it = std::lower_bound(by_off.begin(), by_off.end(), run.vec_off, [](const VecJob& j, size_t o) { return j.off < o; });
+        if (it == by_off.end() || it->off != run.vec_off) return;
+        const uint8_t* p = cbor + run.off;
+        for (size_t i = 0; i < run.count; i++) {
+            const size_t row = run.row0 + i;
+            p = fast_elem(p, cbor + len, row < max_rows ? out + (row * stride + it->col) * 32 : nullptr);
+            if (!p) {
+                ok = false;
+                return;
+            }
+        }
+    });
+    return ok;
+}
+
+// After a structural walk over a pre-scanned file: every element was inside a run and every run was claimed by a vector.
+bool runs_consumed(const Reader& r) {
+    if (!r.runs) return true;
+    if (r.loose) return false;
+    for (const Run& run : *r.runs)
+        if (!run.placed) return false;
+    return true;
+}
+
+// Structure pass over `a` or `b`: array(columns) of array(rows) of [u8;32]; records every column's length and offset.
+bool scan_columns(Reader& r, std::vector<size_t>& rows_out, std::vector<size_t>& off_out) {
     uint64_t nc;
     bool ic;
     if (r.head(nc, ic) != 4) return r.ok = false;
     size_t j = 0;
     while (r.ok && (ic ? !r.at_break() : j < nc)) {
-        uint64_t nr;
-        bool ir;
-        if (r.head(nr, ir) != 4) return r.ok = false;
-        size_t i = 0;
-        while (r.ok && (ir ? !r.at_break() : i < nr)) {
-            r.elem32(out ? out + ((i * stride_cols) + col0 + j) * 32 : nullptr);
-            i++;
-        }
-        if (r.ok && ir) r.skip_break();
-        if (rows_out) rows_out->push_back(i);
+        off_out.push_back(size_t(r.p - r.base));
+        rows_out.push_back(walk_vector(r, nullptr, 0, 0, 0));
         j++;
     }
     if (r.ok && ic) r.skip_break();
     return r.ok;
 }
 
-// One pass over the top-level map.  Shape pass: out == nullptr.
-bool walk(const uint8_t* cbor, size_t len, Shape* shape, uint8_t* out, size_t stride_cols, size_t n_a) {
+// Structure pass over the top-level map of a RawPermutationTrace.
+bool scan_impl(const uint8_t* cbor, size_t len, Shape& shape, std::vector<Run>* runs) {
     Reader r{cbor, cbor + len};
+    r.base = cbor;
+    r.runs = runs;
     uint64_t n;
     bool indef;
     if (r.head(n, indef) != 5) return false;
@@ -160,28 +413,48 @@ bool walk(const uint8_t* cbor, size_t len, Shape* shape, uint8_t* out, size_t st
         std::string key;
         if (!r.text(key)) return false;
         if (key == "a") {
-            walk_columns(r, shape ? &shape->a_rows : nullptr, out, stride_cols, 0);
+            if (seen_a) return false;                       // serde's derived Deserialize: "duplicate field"
+            scan_columns(r, shape.a_rows, shape.a_off);
             seen_a = true;
         } else if (key == "b") {
-            walk_columns(r, shape ? &shape->b_rows : nullptr, out, stride_cols, n_a);
+            if (seen_b) return false;
+            scan_columns(r, shape.b_rows, shape.b_off);
             seen_b = true;
-        } else if (key == "name" && shape) {
-            r.text(shape->name);
+        } else if (key == "name") {
+            r.text(shape.name);
         } else {
             r.skip();
         }
         k++;
     }
-    return r.ok && seen_a && seen_b;
+    return r.ok && seen_a && seen_b && runs_consumed(r);
+}
+
+// Structure pass; with `runs` set it first tries the parallel pre-pass and leaves the placed runs there
+// (empty when the file is not in the regular layout and the serial pass did the work).
+bool scan(const uint8_t* cbor, size_t len, Shape& shape, std::vector<Run>* runs) {
+    if (runs) {
+        if (prescan(cbor, len, *runs)) {
+            Shape s;
+            if (scan_impl(cbor, len, s, runs)) {
+                shape = std::move(s);
+                return true;
+            }
+            if (getenv("LSP_CBOR_DEBUG")) fprintf(stderr, "scan: walk over %zu runs failed\n", runs->size());
+        }
+        runs->clear();
+    }
+    return scan_impl(cbor, len, shape, nullptr);
 }
 
 // ---- RawLookupTrace (trace/src/lookup.rs:10-17) -----------------------------------------------------
 //   { a: Vec<Vec<[u8;32]>>, b: Vec<Vec<Vec<[u8;32]>>>, name, a_filter: Vec<[u8;32]>, b_filter: Vec<Vec<[u8;32]>> }
 struct LookupShape {
-    std::vector<size_t> a_rows;                 // per a column
-    std::vector<std::vector<size_t>> b_rows;    // per table, per column
-    size_t a_filter_len = 0;
-    std::vector<size_t> b_filter_len;           // per table present in the file
+    std::vector<size_t> a_rows, a_off;                  // per a column
+    std::vector<std::vector<size_t>> b_rows, b_off;     // per table, per column
+    size_t a_filter_len = 0, a_filter_off = 0;
+    bool has_a_filter = false;
+    std::vector<size_t> b_filter_len, b_filter_off;     // per table present in the file
     std::string name;
     size_t height() const {                     // get_max_height (:215-228)
         size_t h = 0;
@@ -192,32 +465,15 @@ struct LookupShape {
     }
 };
 
-// array(rows) of [u8;32]; row i goes to out + (i*stride + col)*32 when out != null and i < max_rows.  Returns the length.
-size_t walk_vector(Reader& r, uint8_t* out, size_t stride, size_t col, size_t max_rows) {
-    uint64_t nr;
-    bool ir;
-    if (r.head(nr, ir) != 4) {
-        r.ok = false;
-        return 0;
-    }
-    size_t i = 0;
-    while (r.ok && (ir ? !r.at_break() : i < nr)) {
-        r.elem32(out && i < max_rows ? out + (i * stride + col) * 32 : nullptr);
-        i++;
-    }
-    if (r.ok && ir) r.skip_break();
-    return i;
-}
-
-// One pass over the top-level map.  Decode pass: out != null, with the shape `sh` of the first pass.
-bool walk_lookup(const uint8_t* cbor, size_t len, LookupShape* shape, const LookupShape* sh, uint8_t* out, size_t rows) {
+// Structure pass over the top-level map of a RawLookupTrace: lengths and offsets of every vector.
+bool scan_lookup_impl(const uint8_t* cbor, size_t len, LookupShape& shape, std::vector<Run>* runs) {
     Reader r{cbor, cbor + len};
+    r.base = cbor;
+    r.runs = runs;
     uint64_t n;
     bool indef;
     if (r.head(n, indef) != 5) return false;
-    const size_t n_a = sh ? sh->a_rows.size() : 0, n_t = sh ? sh->b_rows.size() : 0, n_b = (sh && n_t) ? sh->b_rows[0].size() : 0;
-    const size_t stride = n_a + n_t * n_b + 1 + n_t;
-    bool seen_a = false, seen_b = false;
+    bool seen_a = false, seen_b = false, seen_bf = false;
     size_t k = 0;
     while (r.ok && (indef ? !r.at_break() : k < n)) {
         std::string key;
@@ -225,59 +481,56 @@ bool walk_lookup(const uint8_t* cbor, size_t len, LookupShape* shape, const Look
         uint64_t cnt;
         bool ic;
         if (key == "a") {
-            if (r.head(cnt, ic) != 4) return false;
-            size_t j = 0;
-            while (r.ok && (ic ? !r.at_break() : j < cnt)) {
-                size_t l = walk_vector(r, out, stride, j, rows);
-                if (shape) shape->a_rows.push_back(l);
-                j++;
-            }
-            if (r.ok && ic) r.skip_break();
+            if (seen_a) return false;
+            scan_columns(r, shape.a_rows, shape.a_off);
             seen_a = true;
         } else if (key == "b") {
+            if (seen_b) return false;
             if (r.head(cnt, ic) != 4) return false;
             size_t t = 0;
             while (r.ok && (ic ? !r.at_break() : t < cnt)) {
-                uint64_t nc;
-                bool icc;
-                if (r.head(nc, icc) != 4) return false;
-                if (shape) shape->b_rows.emplace_back();
-                size_t j = 0;
-                while (r.ok && (icc ? !r.at_break() : j < nc)) {
-                    size_t l = walk_vector(r, out, stride, n_a + t * n_b + j, rows);
-                    if (shape) shape->b_rows.back().push_back(l);
-                    j++;
-                }
-                if (r.ok && icc) r.skip_break();
+                shape.b_rows.emplace_back();
+                shape.b_off.emplace_back();
+                scan_columns(r, shape.b_rows.back(), shape.b_off.back());
                 t++;
             }
             if (r.ok && ic) r.skip_break();
             seen_b = true;
         } else if (key == "a_filter") {
-            size_t l = walk_vector(r, out, stride, n_a + n_t * n_b, rows);
-            if (shape) shape->a_filter_len = l;
+            if (shape.has_a_filter) return false;
+            shape.a_filter_off = size_t(r.p - r.base);
+            shape.a_filter_len = walk_vector(r, nullptr, 0, 0, 0);
+            shape.has_a_filter = true;
         } else if (key == "b_filter") {
-            if (r.head(cnt, ic) != 4) return false;
-            size_t t = 0;
-            while (r.ok && (ic ? !r.at_break() : t < cnt)) {
-                // filters of tables the file does not have are parsed and dropped
-                size_t l = walk_vector(r, (out && t < n_t) ? out : nullptr, stride, n_a + n_t * n_b + 1 + t, rows);
-                if (shape) shape->b_filter_len.push_back(l);
-                t++;
-            }
-            if (r.ok && ic) r.skip_break();
-        } else if (key == "name" && shape) {
-            r.text(shape->name);
+            if (seen_bf) return false;
+            scan_columns(r, shape.b_filter_len, shape.b_filter_off);
+            seen_bf = true;
+        } else if (key == "name") {
+            r.text(shape.name);
         } else {
             r.skip();
         }
         k++;
     }
-    return r.ok && seen_a && seen_b;
+    return r.ok && seen_a && seen_b && runs_consumed(r);
 }
 
-bool lookup_shape(const uint8_t* cbor, size_t len, LookupShape& s) {
-    if (!walk_lookup(cbor, len, &s, nullptr, nullptr, 0)) return false;
+bool scan_lookup(const uint8_t* cbor, size_t len, LookupShape& shape, std::vector<Run>* runs) {
+    if (runs) {
+        if (prescan(cbor, len, *runs)) {
+            LookupShape s;
+            if (scan_lookup_impl(cbor, len, s, runs)) {
+                shape = std::move(s);
+                return true;
+            }
+        }
+        runs->clear();
+    }
+    return scan_lookup_impl(cbor, len, shape, nullptr);
+}
+
+bool lookup_shape(const uint8_t* cbor, size_t len, LookupShape& s, std::vector<Run>* runs) {
+    if (!scan_lookup(cbor, len, s, runs)) return false;
     if (s.a_rows.empty() || s.b_rows.empty() || s.b_rows[0].empty()) return false;
     for (auto& t : s.b_rows)
         if (t.size() != s.b_rows[0].size()) return false;   // AirLookupConfig::width assumes equal table widths (air_lookup.rs:37-39)
@@ -290,7 +543,8 @@ extern "C" int lsp_cbor_lookup_shape(const uint8_t* cbor, size_t len, size_t* ro
                                      uint32_t* n_b_cols, char* name, size_t name_cap) {
     if (!cbor || !rows || !n_a_cols || !n_tables || !n_b_cols) return LSP_ERR_PARAM;
     LookupShape s;
-    if (!lookup_shape(cbor, len, s)) return LSP_ERR_PARAM;
+    std::vector<Run> runs;
+    if (!lookup_shape(cbor, len, s, &runs)) return LSP_ERR_PARAM;
     *rows = s.height();
     *n_a_cols = uint32_t(s.a_rows.size());
     *n_tables = uint32_t(s.b_rows.size());
@@ -307,11 +561,20 @@ extern "C" int lsp_cbor_lookup_decode(const uint8_t* cbor, size_t len, uint8_t* 
                                       uint32_t n_tables, uint32_t n_b_cols) {
     if (!cbor || !be_rowmajor || rows == 0) return LSP_ERR_PARAM;
     LookupShape s;
-    if (!lookup_shape(cbor, len, s)) return LSP_ERR_PARAM;
+    std::vector<Run> runs;
+    if (!lookup_shape(cbor, len, s, &runs)) return LSP_ERR_PARAM;
     if (s.height() != rows || s.a_rows.size() != n_a_cols || s.b_rows.size() != n_tables || s.b_rows[0].size() != n_b_cols) return LSP_ERR_PARAM;
     const size_t stride = size_t(n_a_cols) + size_t(n_tables) * n_b_cols + 1 + n_tables;
     memset(be_rowmajor, 0, rows * stride * 32);          // `resize` pads columns and filters with zeros (:230-246)
-    if (!walk_lookup(cbor, len, nullptr, &s, be_rowmajor, rows)) return LSP_ERR_PARAM;
+    std::vector<VecJob> jobs;
+    for (size_t j = 0; j < s.a_off.size(); j++) jobs.push_back({s.a_off[j], j});
+    for (size_t t = 0; t < s.b_off.size(); t++)
+        for (size_t j = 0; j < s.b_off[t].size(); j++) jobs.push_back({s.b_off[t][j], size_t(n_a_cols) + t * n_b_cols + j});
+    if (s.has_a_filter) jobs.push_back({s.a_filter_off, size_t(n_a_cols) + size_t(n_tables) * n_b_cols});
+    for (size_t t = 0; t < s.b_filter_off.size() && t < n_tables; t++)     // filters of tables the file does not have are dropped
+        jobs.push_back({s.b_filter_off[t], size_t(n_a_cols) + size_t(n_tables) * n_b_cols + 1 + t});
+    if (!(runs.empty() ? decode_jobs(cbor, len, jobs, be_rowmajor, stride, rows) : decode_runs(cbor, len, runs, jobs, be_rowmajor, stride, rows)))
+        return LSP_ERR_PARAM;
     // `read_file` (:25-41): missing filter entries default to ONE up to the length of the first column they guard
     auto fill_ones = [&](size_t col, size_t from, size_t to) {
         for (size_t i = from; i < to && i < rows; i++) be_rowmajor[(i * stride + col) * 32 + 31] = 1;
@@ -327,7 +590,8 @@ extern "C" int lsp_cbor_lookup_decode(const uint8_t* cbor, size_t len, uint8_t* 
 extern "C" int lsp_cbor_permutation_shape(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_cols, char* name, size_t name_cap) {
     if (!cbor || !rows || !n_cols) return LSP_ERR_PARAM;
     Shape s;
-    if (!walk(cbor, len, &s, nullptr, 0, 0)) return LSP_ERR_PARAM;
+    std::vector<Run> runs;
+    if (!scan(cbor, len, s, &runs)) return LSP_ERR_PARAM;
     if (s.a_rows.empty() || s.a_rows.size() != s.b_rows.size()) return LSP_ERR_PARAM;  // air/src/lib.rs zips a and b ids
     *rows = s.height();
     *n_cols = uint32_t(s.a_rows.size());
@@ -341,11 +605,15 @@ extern "C" int lsp_cbor_permutation_shape(const uint8_t* cbor, size_t len, size_
 
 extern "C" int lsp_cbor_permutation_decode(const uint8_t* cbor, size_t len, uint8_t* be_rowmajor, size_t rows, uint32_t n_cols) {
     if (!cbor || !be_rowmajor || rows == 0 || n_cols == 0) return LSP_ERR_PARAM;
-    size_t r0 = 0;
-    uint32_t c0 = 0;
-    int rc = lsp_cbor_permutation_shape(cbor, len, &r0, &c0, nullptr, 0);
-    if (rc != LSP_OK) return rc;
-    if (r0 != rows || c0 != n_cols) return LSP_ERR_PARAM;
+    Shape s;
+    std::vector<Run> runs;
+    if (!scan(cbor, len, s, &runs)) return LSP_ERR_PARAM;
+    if (s.a_rows.size() != n_cols || s.b_rows.size() != n_cols || s.height() != rows) return LSP_ERR_PARAM;
     memset(be_rowmajor, 0, rows * size_t(2) * n_cols * 32);  // short columns are zero-padded (`resize`, permutation.rs:134-142)
-    return walk(cbor, len, nullptr, be_rowmajor, size_t(2) * n_cols, n_cols) ? LSP_OK : LSP_ERR_PARAM;
+    std::vector<VecJob> jobs;
+    for (size_t j = 0; j < n_cols; j++) jobs.push_back({s.a_off[j], j});
+    for (size_t j = 0; j < n_cols; j++) jobs.push_back({s.b_off[j], size_t(n_cols) + j});
+    const bool ok = runs.empty() ? decode_jobs(cbor, len, jobs, be_rowmajor, size_t(2) * n_cols, rows)
+                                 : decode_runs(cbor, len, runs, jobs, be_rowmajor, size_t(2) * n_cols, rows);
+    return ok ? LSP_OK : LSP_ERR_PARAM;
 }

@@ -146,3 +146,84 @@ def test_lookup_malformed_is_rejected(pkg):
         pkg.read_raw_lookup_trace(cbor2.dumps(obj))
     with pytest.raises(pkg.BackendError):
         pkg.read_raw_lookup_trace(OT.encode_raw_lookup_trace(a, b, af, bf, "x")[:100])
+
+
+# ---- the parallel structure pre-pass (host/cbor.cu: prescan) must be invisible ------------------------------
+def _both_ways(monkeypatch, read, blob):
+    """Reads `blob` with the serial pass and with the parallel pre-pass forced on (tiny chunks, 5 threads)."""
+    monkeypatch.setenv("LSP_CBOR_THREADS", "1")
+    monkeypatch.delenv("LSP_CBOR_PRESCAN_MIN", raising=False)
+    try:
+        serial = read(blob)
+    except Exception as e:                                   # noqa: BLE001
+        serial = type(e)
+    monkeypatch.setenv("LSP_CBOR_THREADS", "5")
+    monkeypatch.setenv("LSP_CBOR_PRESCAN_MIN", "0")
+    try:
+        parallel = read(blob)
+    except Exception as e:                                   # noqa: BLE001
+        parallel = type(e)
+    return serial, parallel
+
+
+def _same(x, y):
+    if isinstance(x, type) or isinstance(y, type):
+        return x is y
+    return all(np.array_equal(a, b) if isinstance(a, np.ndarray) else a == b for a, b in zip(x, y))
+
+
+@pytest.mark.parametrize("rows,c,ragged", [(3, 1, False), (32, 2, False), (33, 2, True), (200, 3, True), (1000, 6, False)])
+def test_parallel_prescan_equals_serial_permutation(pkg, monkeypatch, rows, c, ragged):
+    """32-row columns have the element marker `98 20` as their own head: the pre-pass must notice and step aside."""
+    a, b = OT.synthetic_permutation_input(40 + rows, c, rows)
+    a, b = [list(col) for col in a], [list(col) for col in b]
+    if ragged:
+        a[0] = a[0][:rows // 2]
+        b[-1] = b[-1][:1]
+    a[0][0] = 0x9820 << 8 | 0x18                              # marker-looking bytes inside an element
+    blob = OT.encode_raw_permutation_trace(a, b, "pؘ q")  # ... and inside the name (d8 98 20)
+    serial, parallel = _both_ways(monkeypatch, pkg.read_raw_permutation_trace, blob)
+    assert not isinstance(serial, type) and _same(serial, parallel)
+    assert serial[1:] == (rows, c, "pؘ q")
+    pad = lambda col: list(col) + [0] * (rows - len(col))
+    assert np.array_equal(serial[0], _be([pad(x) for x in a], [pad(x) for x in b], rows))
+
+
+def test_parallel_prescan_equals_serial_lookup(pkg, monkeypatch):
+    a, b, af, bf = OT.synthetic_lookup_input(61, 2, 3, 300, disabled_every=7)
+    blob = OT.encode_raw_lookup_trace(a, b, af[:100], bf[:2], "lk")      # short a_filter, one table's filter missing
+    serial, parallel = _both_ways(monkeypatch, pkg.read_raw_lookup_trace, blob)
+    assert not isinstance(serial, type) and _same(serial, parallel)
+    da, db, daf, dbf, _ = OT.decode_raw_lookup_trace(blob)
+    assert np.array_equal(serial[0], _be_lookup(da, db, daf, dbf, 300))
+
+
+@pytest.mark.parametrize("damage", ["truncate", "flip_head", "byte_strings", "indefinite", "extra_key", "duplicate_key"])
+def test_parallel_prescan_on_irregular_and_malformed_files(pkg, monkeypatch, damage):
+    """Whatever the pre-pass makes of a file, the verdict and the bytes are the serial pass's."""
+    a, b = OT.synthetic_permutation_input(77, 2, 150)
+    blob = bytearray(OT.encode_raw_permutation_trace(a, b, "z"))
+    if damage == "truncate":
+        blob = blob[:len(blob) * 2 // 3]
+    elif damage == "flip_head":
+        k = blob.index(b"\x98\x20", len(blob) // 2)
+        blob[k + 1] = 0x1f                                    # array(31) where an element should be
+    elif damage == "byte_strings":
+        e = lambda x: int(x).to_bytes(32, "big")
+        blob = cbor2.dumps({"a": [[e(x) for x in col] for col in a], "b": [[e(x) for x in col] for col in b], "name": "z"})
+    elif damage == "indefinite":
+        k = blob.index(b"\x98\x20", len(blob) // 3)
+        elem_end = k + 2
+        for _ in range(32):
+            elem_end += 2 if blob[elem_end] == 0x18 else 1
+        blob = blob[:k] + b"\x9f" + blob[k + 2:elem_end] + b"\xff" + blob[elem_end:]
+    elif damage == "extra_key":
+        obj = cbor2.loads(bytes(blob))
+        obj["zz"] = [[list(range(32))] * 40]                  # element-shaped data under a key the struct does not have
+        blob = cbor2.dumps(obj)
+    elif damage == "duplicate_key":
+        tail = bytes(blob[blob.index(b"aa"):blob.index(b"ab")])       # key "a" .. up to key "b": the whole `a` entry
+        blob = bytes([blob[0] + 1]) + bytes(blob[1:]) + tail
+    serial, parallel = _both_ways(monkeypatch, pkg.read_raw_permutation_trace, bytes(blob))
+    assert _same(serial, parallel)
+    assert isinstance(serial, type) == (damage in ("truncate", "flip_head", "duplicate_key"))
