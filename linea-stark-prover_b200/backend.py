@@ -344,21 +344,24 @@ def _c_cfgs(cfgs):
     return arr, keep
 
 
-def read_raw_permutation_trace(blob: bytes):
+def read_raw_permutation_trace(blob: bytes, _fill=None):
     """`RawPermutationTrace::read_file` (trace/src/permutation.rs:17-22) through the library's CBOR parser
-    (host-only entry points: no GPU needed).  Returns (be_bytes uint8[rows*2c*32], rows, n_cols, name)."""
+    (host-only entry points: no GPU needed).  Returns (be_bytes uint8[rows*2c*32], rows, n_cols, name).
+    The decoder writes every byte of the output (values and zero padding); `_fill` lets a test poison it first."""
     lib = ffi.load()
     rows, nc = C.c_size_t(), C.c_uint32()
     name = C.create_string_buffer(256)
     if lib.lsp_cbor_permutation_shape(blob, len(blob), C.byref(rows), C.byref(nc), name, 256) != 0:
         raise BackendError("not a CBOR RawPermutationTrace")
-    out = np.zeros(rows.value * 2 * nc.value * 32, dtype=np.uint8)
+    out = np.empty(rows.value * 2 * nc.value * 32, dtype=np.uint8)
+    if _fill is not None:
+        out[:] = _fill
     if lib.lsp_cbor_permutation_decode(blob, len(blob), out.ctypes.data, rows.value, nc.value) != 0:
         raise BackendError("malformed CBOR RawPermutationTrace")
     return out, rows.value, nc.value, name.value.decode()
 
 
-def read_raw_lookup_trace(blob: bytes):
+def read_raw_lookup_trace(blob: bytes, _fill=None):
     """`RawLookupTrace::read_file` (trace/src/lookup.rs:20-44) through the library's CBOR parser (host only).
     Returns (be_bytes uint8[rows*(n_a + T*n_b + 1 + T)*32], rows, n_a, n_tables, n_b, name)."""
     lib = ffi.load()
@@ -367,10 +370,54 @@ def read_raw_lookup_trace(blob: bytes):
     if lib.lsp_cbor_lookup_shape(blob, len(blob), C.byref(rows), C.byref(na), C.byref(nt), C.byref(nb), name, 256) != 0:
         raise BackendError("not a CBOR RawLookupTrace")
     stride = na.value + nt.value * nb.value + 1 + nt.value
-    out = np.zeros(rows.value * stride * 32, dtype=np.uint8)
+    out = np.empty(rows.value * stride * 32, dtype=np.uint8)
+    if _fill is not None:
+        out[:] = _fill
     if lib.lsp_cbor_lookup_decode(blob, len(blob), out.ctypes.data, rows.value, na.value, nt.value, nb.value) != 0:
         raise BackendError("malformed CBOR RawLookupTrace")
     return out, rows.value, na.value, nt.value, nb.value, name.value.decode()
+
+
+class HostBuffer:
+    """A buffer the library allocated (`lsp_cbor_*_read`); `.array` is a uint8 view, released by `free()` / GC."""
+
+    def __init__(self, lib, ptr, nbytes):
+        self._lib, self._ptr = lib, ptr
+        self.array = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(nbytes,))
+
+    def free(self):
+        if self._ptr:
+            self.array = None
+            self._lib.lsp_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def read_permutation_trace_once(blob: bytes):
+    """`read_raw_permutation_trace` with one structure pass and a library-owned buffer (`lsp_cbor_permutation_read`).
+    Returns (HostBuffer, rows, n_cols, name)."""
+    lib = ffi.load()
+    rows, nc, ptr = C.c_size_t(), C.c_uint32(), C.c_void_p()
+    name = C.create_string_buffer(256)
+    if lib.lsp_cbor_permutation_read(blob, len(blob), C.byref(rows), C.byref(nc), name, 256, C.byref(ptr)) != 0:
+        raise BackendError("malformed CBOR RawPermutationTrace")
+    return HostBuffer(lib, ptr, rows.value * 2 * nc.value * 32), rows.value, nc.value, name.value.decode()
+
+
+def read_lookup_trace_once(blob: bytes):
+    """`read_raw_lookup_trace` through `lsp_cbor_lookup_read`.  Returns (HostBuffer, rows, n_a, n_tables, n_b, name)."""
+    lib = ffi.load()
+    rows, na, nt, nb, ptr = C.c_size_t(), C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_void_p()
+    name = C.create_string_buffer(256)
+    if lib.lsp_cbor_lookup_read(blob, len(blob), C.byref(rows), C.byref(na), C.byref(nt), C.byref(nb), name, 256, C.byref(ptr)) != 0:
+        raise BackendError("malformed CBOR RawLookupTrace")
+    stride = na.value + nt.value * nb.value + 1 + nt.value
+    return HostBuffer(lib, ptr, rows.value * stride * 32), rows.value, na.value, nt.value, nb.value, name.value.decode()
 
 
 def _c_air_cfgs(cfgs):

@@ -335,6 +335,13 @@ bool prescan(const uint8_t* cbor, size_t len, std::vector<Run>& runs) {
     return !runs.empty();
 }
 
+// Zeroes rows [from, rows) of one output column (`resize` pads short columns with zeros).  Full-length columns --
+// the normal case -- cost nothing: there is no blanket memset of the output, every cell is written exactly once,
+// by the decoder or by the padding.
+void pad_column(uint8_t* out, size_t stride, size_t col, size_t from, size_t rows) {
+    for (size_t i = from; i < rows; i++) memset(out + (i * stride + col) * 32, 0, 32);
+}
+
 // One vector of the file (found by the structure pass) and the output column it fills.
 struct VecJob {
     size_t off, col;
@@ -537,6 +544,58 @@ bool lookup_shape(const uint8_t* cbor, size_t len, LookupShape& s, std::vector<R
     return true;
 }
 
+// Fills the row-major output of a scanned RawLookupTrace (values, zero padding, default filters).
+bool fill_lookup(const uint8_t* cbor, size_t len, const LookupShape& s, const std::vector<Run>& runs, uint8_t* out, size_t rows) {
+    const size_t n_a = s.a_rows.size(), n_t = s.b_rows.size(), n_b = s.b_rows[0].size();
+    const size_t stride = n_a + n_t * n_b + 1 + n_t, col_af = n_a + n_t * n_b;
+    // `resize` pads columns and filters with zeros (:230-246)
+    for (size_t j = 0; j < n_a; j++) pad_column(out, stride, j, s.a_rows[j], rows);
+    for (size_t t = 0; t < n_t; t++)
+        for (size_t j = 0; j < n_b; j++) pad_column(out, stride, n_a + t * n_b + j, s.b_rows[t][j], rows);
+    pad_column(out, stride, col_af, s.has_a_filter ? s.a_filter_len : 0, rows);
+    for (size_t t = 0; t < n_t; t++) pad_column(out, stride, col_af + 1 + t, t < s.b_filter_len.size() ? s.b_filter_len[t] : 0, rows);
+    std::vector<VecJob> jobs;
+    for (size_t j = 0; j < n_a; j++) jobs.push_back({s.a_off[j], j});
+    for (size_t t = 0; t < n_t; t++)
+        for (size_t j = 0; j < n_b; j++) jobs.push_back({s.b_off[t][j], n_a + t * n_b + j});
+    if (s.has_a_filter) jobs.push_back({s.a_filter_off, col_af});
+    for (size_t t = 0; t < s.b_filter_off.size() && t < n_t; t++)     // filters of tables the file does not have are dropped
+        jobs.push_back({s.b_filter_off[t], col_af + 1 + t});
+    if (!(runs.empty() ? decode_jobs(cbor, len, jobs, out, stride, rows) : decode_runs(cbor, len, runs, jobs, out, stride, rows))) return false;
+    // `read_file` (:25-41): missing filter entries default to ONE up to the length of the first column they guard
+    auto fill_ones = [&](size_t col, size_t from, size_t to) {
+        for (size_t i = from; i < to && i < rows; i++) out[(i * stride + col) * 32 + 31] = 1;
+    };
+    fill_ones(col_af, s.a_filter_len, s.a_rows[0]);
+    for (size_t t = 0; t < n_t; t++) fill_ones(col_af + 1 + t, t < s.b_filter_len.size() ? s.b_filter_len[t] : 0, s.b_rows[t][0]);
+    return true;
+}
+
+// The same for a scanned RawPermutationTrace.
+bool fill_permutation(const uint8_t* cbor, size_t len, const Shape& s, const std::vector<Run>& runs, uint8_t* out, size_t rows) {
+    const size_t nc = s.a_rows.size();
+    std::vector<VecJob> jobs;
+    for (size_t j = 0; j < nc; j++) {                        // short columns are zero-padded (`resize`, permutation.rs:134-142)
+        pad_column(out, 2 * nc, j, s.a_rows[j], rows);
+        pad_column(out, 2 * nc, nc + j, s.b_rows[j], rows);
+        jobs.push_back({s.a_off[j], j});
+        jobs.push_back({s.b_off[j], nc + j});
+    }
+    return runs.empty() ? decode_jobs(cbor, len, jobs, out, 2 * nc, rows) : decode_runs(cbor, len, runs, jobs, out, 2 * nc, rows);
+}
+
+bool permutation_shape(const uint8_t* cbor, size_t len, Shape& s, std::vector<Run>* runs) {
+    if (!scan(cbor, len, s, runs)) return false;
+    return !s.a_rows.empty() && s.a_rows.size() == s.b_rows.size();   // air/src/lib.rs zips a and b ids
+}
+
+void copy_name(const std::string& from, char* name, size_t name_cap) {
+    if (!name || !name_cap) return;
+    const size_t n = from.size() < name_cap - 1 ? from.size() : name_cap - 1;
+    memcpy(name, from.data(), n);
+    name[n] = 0;
+}
+
 }  // namespace
 
 extern "C" int lsp_cbor_lookup_shape(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_a_cols, uint32_t* n_tables,
@@ -549,11 +608,7 @@ extern "C" int lsp_cbor_lookup_shape(const uint8_t* cbor, size_t len, size_t* ro
     *n_a_cols = uint32_t(s.a_rows.size());
     *n_tables = uint32_t(s.b_rows.size());
     *n_b_cols = uint32_t(s.b_rows[0].size());
-    if (name && name_cap) {
-        size_t n = s.name.size() < name_cap - 1 ? s.name.size() : name_cap - 1;
-        memcpy(name, s.name.data(), n);
-        name[n] = 0;
-    }
+    copy_name(s.name, name, name_cap);
     return LSP_OK;
 }
 
@@ -564,26 +619,28 @@ extern "C" int lsp_cbor_lookup_decode(const uint8_t* cbor, size_t len, uint8_t* 
     std::vector<Run> runs;
     if (!lookup_shape(cbor, len, s, &runs)) return LSP_ERR_PARAM;
     if (s.height() != rows || s.a_rows.size() != n_a_cols || s.b_rows.size() != n_tables || s.b_rows[0].size() != n_b_cols) return LSP_ERR_PARAM;
-    const size_t stride = size_t(n_a_cols) + size_t(n_tables) * n_b_cols + 1 + n_tables;
-    memset(be_rowmajor, 0, rows * stride * 32);          // `resize` pads columns and filters with zeros (:230-246)
-    std::vector<VecJob> jobs;
-    for (size_t j = 0; j < s.a_off.size(); j++) jobs.push_back({s.a_off[j], j});
-    for (size_t t = 0; t < s.b_off.size(); t++)
-        for (size_t j = 0; j < s.b_off[t].size(); j++) jobs.push_back({s.b_off[t][j], size_t(n_a_cols) + t * n_b_cols + j});
-    if (s.has_a_filter) jobs.push_back({s.a_filter_off, size_t(n_a_cols) + size_t(n_tables) * n_b_cols});
-    for (size_t t = 0; t < s.b_filter_off.size() && t < n_tables; t++)     // filters of tables the file does not have are dropped
-        jobs.push_back({s.b_filter_off[t], size_t(n_a_cols) + size_t(n_tables) * n_b_cols + 1 + t});
-    if (!(runs.empty() ? decode_jobs(cbor, len, jobs, be_rowmajor, stride, rows) : decode_runs(cbor, len, runs, jobs, be_rowmajor, stride, rows)))
+    return fill_lookup(cbor, len, s, runs, be_rowmajor, rows) ? LSP_OK : LSP_ERR_PARAM;
+}
+
+extern "C" int lsp_cbor_lookup_read(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_a_cols, uint32_t* n_tables,
+                                    uint32_t* n_b_cols, char* name, size_t name_cap, uint8_t** be_rowmajor_out) {
+    if (!cbor || !rows || !n_a_cols || !n_tables || !n_b_cols || !be_rowmajor_out) return LSP_ERR_PARAM;
+    LookupShape s;
+    std::vector<Run> runs;
+    if (!lookup_shape(cbor, len, s, &runs) || s.height() == 0) return LSP_ERR_PARAM;
+    const size_t h = s.height(), stride = s.a_rows.size() + s.b_rows.size() * (s.b_rows[0].size() + 1) + 1;
+    uint8_t* out = static_cast<uint8_t*>(malloc(h * stride * 32));
+    if (!out) return LSP_ERR_NOMEM;
+    if (!fill_lookup(cbor, len, s, runs, out, h)) {
+        free(out);
         return LSP_ERR_PARAM;
-    // `read_file` (:25-41): missing filter entries default to ONE up to the length of the first column they guard
-    auto fill_ones = [&](size_t col, size_t from, size_t to) {
-        for (size_t i = from; i < to && i < rows; i++) be_rowmajor[(i * stride + col) * 32 + 31] = 1;
-    };
-    fill_ones(size_t(n_a_cols) + size_t(n_tables) * n_b_cols, s.a_filter_len, s.a_rows[0]);
-    for (uint32_t t = 0; t < n_tables; t++) {
-        size_t have = t < s.b_filter_len.size() ? s.b_filter_len[t] : 0;
-        fill_ones(size_t(n_a_cols) + size_t(n_tables) * n_b_cols + 1 + t, have, s.b_rows[t][0]);
     }
+    *rows = h;
+    *n_a_cols = uint32_t(s.a_rows.size());
+    *n_tables = uint32_t(s.b_rows.size());
+    *n_b_cols = uint32_t(s.b_rows[0].size());
+    copy_name(s.name, name, name_cap);
+    *be_rowmajor_out = out;
     return LSP_OK;
 }
 
@@ -591,15 +648,10 @@ extern "C" int lsp_cbor_permutation_shape(const uint8_t* cbor, size_t len, size_
     if (!cbor || !rows || !n_cols) return LSP_ERR_PARAM;
     Shape s;
     std::vector<Run> runs;
-    if (!scan(cbor, len, s, &runs)) return LSP_ERR_PARAM;
-    if (s.a_rows.empty() || s.a_rows.size() != s.b_rows.size()) return LSP_ERR_PARAM;  // air/src/lib.rs zips a and b ids
+    if (!permutation_shape(cbor, len, s, &runs)) return LSP_ERR_PARAM;
     *rows = s.height();
     *n_cols = uint32_t(s.a_rows.size());
-    if (name && name_cap) {
-        size_t n = s.name.size() < name_cap - 1 ? s.name.size() : name_cap - 1;
-        memcpy(name, s.name.data(), n);
-        name[n] = 0;
-    }
+    copy_name(s.name, name, name_cap);
     return LSP_OK;
 }
 
@@ -607,13 +659,29 @@ extern "C" int lsp_cbor_permutation_decode(const uint8_t* cbor, size_t len, uint
     if (!cbor || !be_rowmajor || rows == 0 || n_cols == 0) return LSP_ERR_PARAM;
     Shape s;
     std::vector<Run> runs;
-    if (!scan(cbor, len, s, &runs)) return LSP_ERR_PARAM;
-    if (s.a_rows.size() != n_cols || s.b_rows.size() != n_cols || s.height() != rows) return LSP_ERR_PARAM;
-    memset(be_rowmajor, 0, rows * size_t(2) * n_cols * 32);  // short columns are zero-padded (`resize`, permutation.rs:134-142)
-    std::vector<VecJob> jobs;
-    for (size_t j = 0; j < n_cols; j++) jobs.push_back({s.a_off[j], j});
-    for (size_t j = 0; j < n_cols; j++) jobs.push_back({s.b_off[j], size_t(n_cols) + j});
-    const bool ok = runs.empty() ? decode_jobs(cbor, len, jobs, be_rowmajor, size_t(2) * n_cols, rows)
-                                 : decode_runs(cbor, len, runs, jobs, be_rowmajor, size_t(2) * n_cols, rows);
-    return ok ? LSP_OK : LSP_ERR_PARAM;
+    if (!permutation_shape(cbor, len, s, &runs)) return LSP_ERR_PARAM;
+    if (s.a_rows.size() != n_cols || s.height() != rows) return LSP_ERR_PARAM;
+    return fill_permutation(cbor, len, s, runs, be_rowmajor, rows) ? LSP_OK : LSP_ERR_PARAM;
 }
+
+extern "C" int lsp_cbor_permutation_read(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_cols, char* name, size_t name_cap,
+                                         uint8_t** be_rowmajor_out) {
+    if (!cbor || !rows || !n_cols || !be_rowmajor_out) return LSP_ERR_PARAM;
+    Shape s;
+    std::vector<Run> runs;
+    if (!permutation_shape(cbor, len, s, &runs) || s.height() == 0) return LSP_ERR_PARAM;
+    const size_t h = s.height(), nc = s.a_rows.size();
+    uint8_t* out = static_cast<uint8_t*>(malloc(h * 2 * nc * 32));
+    if (!out) return LSP_ERR_NOMEM;
+    if (!fill_permutation(cbor, len, s, runs, out, h)) {
+        free(out);
+        return LSP_ERR_PARAM;
+    }
+    *rows = h;
+    *n_cols = uint32_t(nc);
+    copy_name(s.name, name, name_cap);
+    *be_rowmajor_out = out;
+    return LSP_OK;
+}
+
+extern "C" void lsp_host_free(void* p) { free(p); }

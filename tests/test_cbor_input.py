@@ -30,7 +30,7 @@ def test_ragged_columns_are_zero_padded(pkg):
     """`resize` (trace/src/permutation.rs:134-142): short columns grow to the tallest with zeros."""
     a = [[1, 2, 3, 4], [5, 6]]
     b = [[7], [8, 9, 10]]
-    be, rows, nc, _ = pkg.read_raw_permutation_trace(OT.encode_raw_permutation_trace(a, b, "r"))
+    be, rows, nc, _ = pkg.read_raw_permutation_trace(OT.encode_raw_permutation_trace(a, b, "r"), _fill=0xEE)
     assert (rows, nc) == (4, 2)
     assert np.array_equal(be, _be([a[0], a[1] + [0, 0]], [b[0] + [0, 0, 0], b[1] + [0]], 4))
 
@@ -127,7 +127,7 @@ def test_lookup_default_filters_and_padding(pkg):
     b = [[[5, 6, 7, 9, 9], [1, 2, 3, 9, 9]],         # table 0: 5 rows  -> trace height 5
          [[5, 5], [1, 1]]]                           # table 1: 2 rows
     blob = OT.encode_raw_lookup_trace(a, b, [0], [[1, 0]], "d")   # a_filter has 1 entry, b_filter only for table 0
-    be, rows, na, nt, nb, _ = pkg.read_raw_lookup_trace(blob)
+    be, rows, na, nt, nb, _ = pkg.read_raw_lookup_trace(blob, _fill=0xEE)
     assert (rows, na, nt, nb) == (5, 2, 2, 2)
     da, db, daf, dbf, _ = OT.decode_raw_lookup_trace(blob)
     assert daf == [0, 1, 1, 0, 0]                    # given, ones up to len(a[0]) = 3, zero padding
@@ -182,7 +182,8 @@ def test_parallel_prescan_equals_serial_permutation(pkg, monkeypatch, rows, c, r
         b[-1] = b[-1][:1]
     a[0][0] = 0x9820 << 8 | 0x18                              # marker-looking bytes inside an element
     blob = OT.encode_raw_permutation_trace(a, b, "pؘ q")  # ... and inside the name (d8 98 20)
-    serial, parallel = _both_ways(monkeypatch, pkg.read_raw_permutation_trace, blob)
+    poisoned = lambda x: pkg.read_raw_permutation_trace(x, _fill=0xCD)      # every output byte must be written
+    serial, parallel = _both_ways(monkeypatch, poisoned, blob)
     assert not isinstance(serial, type) and _same(serial, parallel)
     assert serial[1:] == (rows, c, "pؘ q")
     pad = lambda col: list(col) + [0] * (rows - len(col))
@@ -192,7 +193,7 @@ def test_parallel_prescan_equals_serial_permutation(pkg, monkeypatch, rows, c, r
 def test_parallel_prescan_equals_serial_lookup(pkg, monkeypatch):
     a, b, af, bf = OT.synthetic_lookup_input(61, 2, 3, 300, disabled_every=7)
     blob = OT.encode_raw_lookup_trace(a, b, af[:100], bf[:2], "lk")      # short a_filter, one table's filter missing
-    serial, parallel = _both_ways(monkeypatch, pkg.read_raw_lookup_trace, blob)
+    serial, parallel = _both_ways(monkeypatch, lambda x: pkg.read_raw_lookup_trace(x, _fill=0xCD), blob)
     assert not isinstance(serial, type) and _same(serial, parallel)
     da, db, daf, dbf, _ = OT.decode_raw_lookup_trace(blob)
     assert np.array_equal(serial[0], _be_lookup(da, db, daf, dbf, 300))
@@ -227,3 +228,31 @@ def test_parallel_prescan_on_irregular_and_malformed_files(pkg, monkeypatch, dam
     serial, parallel = _both_ways(monkeypatch, pkg.read_raw_permutation_trace, bytes(blob))
     assert _same(serial, parallel)
     assert isinstance(serial, type) == (damage in ("truncate", "flip_head", "duplicate_key"))
+
+
+def test_single_pass_read_equals_shape_plus_decode(pkg, monkeypatch):
+    """`lsp_cbor_*_read` (library-allocated buffer, one structure pass) == `_shape` + `_decode`, serial and parallel."""
+    a, b = OT.synthetic_permutation_input(5, 3, 120)
+    a[1] = a[1][:70]
+    pblob = OT.encode_raw_permutation_trace(a, b, "one")
+    la, lb, laf, lbf = OT.synthetic_lookup_input(6, 2, 2, 90, disabled_every=5)
+    lblob = OT.encode_raw_lookup_trace(la, lb, laf[:10], lbf[:1], "two")
+    for threads, prescan in (("1", None), ("6", "0")):
+        monkeypatch.setenv("LSP_CBOR_THREADS", threads)
+        if prescan is None:
+            monkeypatch.delenv("LSP_CBOR_PRESCAN_MIN", raising=False)
+        else:
+            monkeypatch.setenv("LSP_CBOR_PRESCAN_MIN", prescan)
+        want = pkg.read_raw_permutation_trace(pblob, _fill=0x5A)
+        buf, *meta = pkg.read_permutation_trace_once(pblob)
+        assert tuple(meta) == want[1:] and np.array_equal(buf.array, want[0])
+        buf.free()
+        want = pkg.read_raw_lookup_trace(lblob, _fill=0x5A)
+        buf, *meta = pkg.read_lookup_trace_once(lblob)
+        assert tuple(meta) == want[1:] and np.array_equal(buf.array, want[0])
+        buf.free()
+    for bad in (pblob[:200], b"\x00", lblob[:-3]):
+        with pytest.raises(pkg.BackendError):
+            pkg.read_permutation_trace_once(bad)
+    with pytest.raises(pkg.BackendError):
+        pkg.read_lookup_trace_once(lblob[:300])

@@ -59,4 +59,4 @@ def test_driver_proves_cbor_files_like_main(pkg, tmp_path):
 def test_driver_fails_loudly_on_bad_input(tmp_path):
     (tmp_path / "junk.bin").write_bytes(b"\x00\x01\x02")
     r = subprocess.run([str(EXE), "--permutation", str(tmp_path / "junk.bin")], capture_output=True, text=True, timeout=120)
-    assert r.returncode != 0 and "lsp_cbor_permutation_shape" in r.stderr
+    assert r.returncode != 0 and "lsp_cbor_permutation_read" in r.stderr

@@ -1,6 +1,7 @@
 """Host-side throughput of the CBOR reader (lsp_cbor_permutation_shape/_decode) on a cfg-5-shaped file:
 6+6 columns of 2^LOG_N rows, every [u8;32] written the way serde writes it (a CBOR array of 32 small ints).
-Runs without a GPU (the parser is host-only).   python tools/cbor_bench.py [LOG_N]"""
+Runs without a GPU (the parser is host-only).   python tools/cbor_bench.py [LOG_N] [--write FILE]
+With --write the file is kept, e.g. for `lsp_prove --permutation FILE` (BASELINE configs[4] stand-in)."""
 import sys
 import time
 
@@ -40,7 +41,13 @@ def column_blob(vals: np.ndarray) -> bytes:
 
 
 def main():
-    log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    argv = [a for a in sys.argv[1:]]
+    write = None
+    if "--write" in argv:
+        k = argv.index("--write")
+        write = argv[k + 1]
+        del argv[k:k + 2]
+    log_n = int(argv[0]) if argv else 16
     n, c = 1 << log_n, 6
     rng = np.random.default_rng(1)
     cols = [rng.integers(0, 256, size=(n, 32), dtype=np.uint8) for _ in range(c)]
@@ -50,6 +57,9 @@ def main():
     a = b"".join(column_blob(col) for col in cols)
     b = b"".join(column_blob(col[perm]) for col in cols)
     blob = head(5, 3) + head(3, 1) + b"a" + head(4, c) + a + head(3, 1) + b"b" + head(4, c) + b + head(3, 4) + b"name" + head(3, 3) + b"mxp"
+    if write:
+        with open(write, "wb") as f:
+            f.write(blob)
     pkg = g.load_package()
     import ctypes as C
     lib = pkg.ffi.load()
