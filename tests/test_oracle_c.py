@@ -62,3 +62,61 @@ def test_c_gen_trace_satisfies_air():
     cfgs = [OA.AirPermutationConfig.standard(3)]
     assert OA.check_constraints(cfgs, trace, publics)
     assert trace[-1][-1] == 1
+
+
+# Python oracle's error names <-> the C port's codes (and LSP_VERIFY_* of include/lsp_b200.h)
+_REASON_CODES = {"InvalidProofShape": {1}, "InputError(MerkleRootMismatch)": {2, 3}, "CommitPhaseMmcsError": {4},
+                 "FinalPolyMismatch": {5}, "InvalidPowWitness": {6}, "OodEvaluationMismatch": {7}}
+
+
+def test_c_verifier_names_the_same_failing_check_as_the_python_verifier(p2params):
+    """The two restatements of `verify` must agree not only on accept/reject but on WHICH check fails, for every kind
+    of damage a structured proof can carry (the device verifier is then compared with the C port code for code)."""
+    import copy
+    cport.set_poseidon2(p2params)
+    log_n, c = 5, 2
+    fri = dict(log_blowup=2, log_final_poly_len=1, num_queries=6, proof_of_work_bits=3)
+    rng = F.SplitMix64(99)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    cfgs, trace = OT.build_trace([OT.synthetic_permutation_input(9, c, 1 << log_n)], alpha, delta)
+    ofri = OS.FriConfig(**fri)
+    dbg = {}
+    good = OS.prove(p2params, ofri, cfgs, trace, [alpha, delta], dbg)
+    idx = dbg["query_indices"]
+    w = OA.air_width(cfgs)
+    pub = np.array([F.to_mont_limbs(alpha), F.to_mont_limbs(delta)], dtype=np.uint64)
+
+    def both(proof, use_cfgs=cfgs):
+        try:
+            OS.verify(p2params, ofri, use_cfgs, proof, [alpha, delta])
+            name = None
+        except OS.VerificationError as e:
+            name = str(e)
+        code = cport.verify_limbs(ofri, log_n, w, use_cfgs, pub, flat_from_dict(proof, idx))
+        return name, code
+
+    assert both(good) == (None, 0)
+    bump = lambda v: (v + 1) % F.R_MOD
+    damage = {}
+    p = copy.deepcopy(good); q = p["opening_proof"]["query_proofs"][2]
+    q["input_proof"][0]["opened_values"][0][1] = bump(q["input_proof"][0]["opened_values"][0][1]); damage["trace row"] = p
+    p = copy.deepcopy(good); q = p["opening_proof"]["query_proofs"][0]
+    q["input_proof"][0]["opening_proof"][-1] = bump(q["input_proof"][0]["opening_proof"][-1]); damage["trace path"] = p
+    p = copy.deepcopy(good); q = p["opening_proof"]["query_proofs"][5]
+    q["input_proof"][1]["opened_values"][1][0] = bump(q["input_proof"][1]["opened_values"][1][0]); damage["quotient row"] = p
+    p = copy.deepcopy(good); q = p["opening_proof"]["query_proofs"][1]
+    q["commit_phase_openings"][0]["sibling_value"] = bump(q["commit_phase_openings"][0]["sibling_value"]); damage["fri sibling"] = p
+    p = copy.deepcopy(good); q = p["opening_proof"]["query_proofs"][3]
+    q["commit_phase_openings"][-1]["opening_proof"][0] = bump(q["commit_phase_openings"][-1]["opening_proof"][0]); damage["fri path"] = p
+    p = copy.deepcopy(good); p["opened_values"]["trace_next"][0] = bump(p["opened_values"]["trace_next"][0]); damage["opened value"] = p
+    p = copy.deepcopy(good); p["opening_proof"]["pow_witness"] = bump(p["opening_proof"]["pow_witness"]); damage["pow witness"] = p
+    seen = set()
+    for what, proof in damage.items():
+        name, code = both(proof)
+        assert name is not None and code in _REASON_CODES[name], (what, name, code)
+        seen.add(name)
+    c0 = cfgs[0]
+    swapped = [OA.AirPermutationConfig(list(reversed(c0.a_columns_ids)), c0.b_columns_ids, c0.b_inverse_id, c0.check_id)]
+    name, code = both(good, swapped)
+    assert (name, code) == ("OodEvaluationMismatch", 7)
+    assert {"InputError(MerkleRootMismatch)", "CommitPhaseMmcsError"} <= seen
