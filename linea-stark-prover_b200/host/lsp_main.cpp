@@ -14,7 +14,9 @@
 // written in a compiled language would use, and it cannot fall back to anything -- no device, no proof.
 //
 //   lsp_prove [--lookup f.cbor]... [--permutation f.cbor]... [--seed S] [--log-blowup 3] [--queries 33]
-//             [--pow-bits 0] [--sbox-d 5] [--device 0] [--out proof.bin] [--repeat 1]
+//             [--pow-bits 0] [--sbox-d 5] [--device 0] [--gpus 1] [--out proof.bin] [--repeat 1]
+//   --gpus N: ONE proof sharded over devices device..device+N-1 (one host thread and one lsp_ctx per GPU, NCCL
+//   between them: lsp_prove_air_sharded_dev); every rank builds the witness on its own device from the same parsed bytes.
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -22,6 +24,7 @@
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <fcntl.h>
@@ -113,13 +116,39 @@ struct LookupIds {  // storage behind one lsp_lookup_air_cfg
     std::vector<uint32_t> a, b, bf, bi, occ;
 };
 
+// One parsed input file: the big-endian bytes of its columns (host) and what they are.
+struct SubTrace {
+    bool lookup = false;
+    std::string name;
+    size_t rows = 0;
+    uint32_t na = 0, nt = 0, nb = 0;   // lookup: a columns, tables, b columns per table; permutation: na = columns per side
+    uint8_t* be = nullptr;
+};
+
+// One GPU of the job.
+struct Rank {
+    int device = 0;
+    lsp_ctx* ctx = nullptr;
+    lsp_comm* comm = nullptr;
+    lsp_mat* trace = nullptr;
+};
+
+// body(rank) on one host thread per rank (the library wants one ctx per thread); rank 0 runs on the caller.
+template <class F>
+void on_all_ranks(std::vector<Rank>& ranks, F body) {
+    std::vector<std::thread> pool;
+    for (size_t k = 1; k < ranks.size(); k++) pool.emplace_back([&, k]() { body(ranks[k], int(k)); });
+    body(ranks[0], 0);
+    for (auto& t : pool) t.join();
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     std::vector<std::string> lookups, perms;
     std::string out_path;
     uint64_t seed = 0xB200;
-    int device = 0, sbox_d = 5, repeat = 1;
+    int device = 0, sbox_d = 5, repeat = 1, gpus = 1;
     lsp_fri_config fri = {3, 0, 33, 0};  // bin/src/main.rs:58-64
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
@@ -138,6 +167,7 @@ int main(int argc, char** argv) {
         else if (a == "--pow-bits") fri.proof_of_work_bits = uint32_t(atoi(need("--pow-bits")));
         else if (a == "--sbox-d") sbox_d = atoi(need("--sbox-d"));
         else if (a == "--device") device = atoi(need("--device"));
+        else if (a == "--gpus") gpus = atoi(need("--gpus"));
         else if (a == "--out") out_path = need("--out");
         else if (a == "--repeat") repeat = atoi(need("--repeat"));
         else {
@@ -146,16 +176,14 @@ int main(int argc, char** argv) {
         }
     }
     if (lookups.empty() && perms.empty()) {
-        fprintf(stderr, "usage: lsp_prove [--lookup f.cbor]... [--permutation f.cbor]... [--seed S] [--out proof.bin]\n");
+        fprintf(stderr, "usage: lsp_prove [--lookup f.cbor]... [--permutation f.cbor]... [--seed S] [--gpus N] [--out proof.bin]\n");
+        return 2;
+    }
+    if (gpus < 1 || (gpus & (gpus - 1)) || (1u << fri.log_blowup) < unsigned(gpus)) {
+        fprintf(stderr, "--gpus must be a power of two no larger than the blowup (2^%u)\n", fri.log_blowup);
         return 2;
     }
 
-    lsp_ctx* ctx = nullptr;
-    int rc = lsp_ctx_create(device, &ctx);
-    if (rc != 0) {
-        fprintf(stderr, "lsp_ctx_create(%d) failed (%d): a CUDA device is required, there is no CPU path\n", device, rc);
-        return 1;
-    }
     SplitMix rng{seed};
     uint64_t publics[2][4];
     rng.fr(publics[0]);  // alpha  (main.rs:30)
@@ -164,7 +192,6 @@ int main(int argc, char** argv) {
            (unsigned long long)publics[1][2], (unsigned long long)publics[1][1], (unsigned long long)publics[1][0]);
     printf("Challenge alpha: 0x%016llx%016llx%016llx%016llx (Montgomery limbs)\n", (unsigned long long)publics[0][3],
            (unsigned long long)publics[0][2], (unsigned long long)publics[0][1], (unsigned long long)publics[0][0]);
-
     // ---- Perm::new_from_rng(8, 22, &mut rng) (main.rs:49): 4x3 initial, 4x3 terminal, 22 internal constants
     std::vector<uint64_t> consts((8 * 3 + 22) * 4);
     for (size_t i = 0; i < consts.size() / 4; i++) rng.fr(&consts[4 * i]);
@@ -172,107 +199,127 @@ int main(int argc, char** argv) {
     memcpy(diag[0], ONE_MONT, 32);
     memcpy(diag[1], ONE_MONT, 32);
     memcpy(diag[2], TWO_MONT, 32);
-    CHECK(ctx, lsp_set_poseidon2(ctx, 3, sbox_d, 8, 22, consts.data(), &diag[0][0]));
+
+    // ---- one context per GPU; with several, an NCCL communicator between them
+    std::vector<Rank> ranks(static_cast<size_t>(gpus));
+    uint8_t nccl_id[128] = {0};
+    if (gpus > 1 && lsp_nccl_unique_id(nccl_id) != 0) {
+        fprintf(stderr, "lsp_nccl_unique_id failed: libnccl.so.2 is needed for --gpus > 1\n");
+        return 1;
+    }
+    on_all_ranks(ranks, [&](Rank& r, int k) {
+        r.device = device + k;
+        int rc = lsp_ctx_create(r.device, &r.ctx);
+        if (rc != 0) {
+            fprintf(stderr, "lsp_ctx_create(%d) failed (%d): a CUDA device is required, there is no CPU path\n", r.device, rc);
+            exit(1);
+        }
+        CHECK(r.ctx, lsp_set_poseidon2(r.ctx, 3, sbox_d, 8, 22, consts.data(), &diag[0][0]));
+        if (gpus > 1) CHECK(r.ctx, lsp_comm_init_nccl(r.ctx, k, gpus, nccl_id, &r.comm));
+    });
+    lsp_ctx* ctx = ranks[0].ctx;
 
     // One pass of main's body.  --repeat N runs it N times in one process: the first pass pays for the CUDA context,
     // the memory pool and the twiddle / selector tables; later passes are what a long-running prover sees.
     auto run_once = [&]() -> int {
-        // ---- push_traces: lookups first, then permutations; configs shifted by the running width (trace/src/lib.rs:62-92)
-        printf("Generating trace...\n");
         using clk = std::chrono::steady_clock;
         auto ms_since = [](clk::time_point t0) { return std::chrono::duration<double, std::milli>(clk::now() - t0).count(); };
-        double t_read = 0, t_cbor = 0, t_witness = 0;
-        size_t cbor_bytes = 0;
+        // ---- read_file (main.rs:37-41): parse every input once on the host
+        printf("Generating trace...\n");
         const clk::time_point t_gen0 = clk::now();
-        std::vector<lsp_mat*> parts;
+        double t_read = 0, t_cbor = 0;
+        size_t cbor_bytes = 0;
+        std::vector<SubTrace> subs;
+        auto load = [&](const std::string& path, bool is_lookup) {
+            clk::time_point t0 = clk::now();
+            MappedFile blob(path);
+            t_read += ms_since(t0);
+            cbor_bytes += blob.size();
+            SubTrace st;
+            st.lookup = is_lookup;
+            char name[128] = {0};
+            t0 = clk::now();
+            if (is_lookup)
+                CHECK(ctx, lsp_cbor_lookup_read(blob.data(), blob.size(), &st.rows, &st.na, &st.nt, &st.nb, name, sizeof name, &st.be));
+            else
+                CHECK(ctx, lsp_cbor_permutation_read(blob.data(), blob.size(), &st.rows, &st.na, name, sizeof name, &st.be));
+            t_cbor += ms_since(t0);
+            st.name = name;
+            subs.push_back(st);
+        };
+        for (auto& f : lookups) load(f, true);      // push_traces: lookups first, then permutations (trace/src/lib.rs:62-92)
+        for (auto& f : perms) load(f, false);
+        struct FreeSubs {
+            std::vector<SubTrace>& v;
+            ~FreeSubs() {
+                for (auto& st : v) lsp_host_free(st.be);
+            }
+        } free_subs{subs};
+
+        // ---- AIR configs, shifted by the running width exactly as `cfg.shift(self.columns.len())` does
         std::vector<lsp_lookup_air_cfg> lcfg;
         std::vector<lsp_perm_air_cfg> pcfg;
         std::vector<LookupIds> lids(lookups.size());
         std::vector<std::vector<uint32_t>> pa(perms.size()), pb(perms.size());
         uint32_t col = 0;
-        size_t height = 0;
-        for (size_t k = 0; k < lookups.size(); k++) {
-            clk::time_point t0 = clk::now();
-            MappedFile blob(lookups[k]);
-            t_read += ms_since(t0);
-            cbor_bytes += blob.size();
-            size_t rows = 0;
-            uint32_t na = 0, nt = 0, nb = 0;
-            char name[128];
-            t0 = clk::now();
-            uint8_t* be_raw = nullptr;
-            CHECK(ctx, lsp_cbor_lookup_read(blob.data(), blob.size(), &rows, &na, &nt, &nb, name, sizeof name, &be_raw));
-            HostBytes be(be_raw);
-            t_cbor += ms_since(t0);
-            lsp_mat* m = nullptr;
-            t0 = clk::now();
-            CHECK(ctx, lsp_lookup_trace_be(ctx, be.data(), rows, na, nt, nb, publics, &m));
-            CHECK(ctx, lsp_ctx_sync(ctx));
-            t_witness += ms_since(t0);
-            parts.push_back(m);
-            // get_air_lookup_config (trace/src/lookup.rs:178-214), shifted by `col`
-            LookupIds& L = lids[k];
-            for (uint32_t j = 0; j < na; j++) L.a.push_back(col + j);
-            for (uint32_t t = 0; t < nt; t++)
-                for (uint32_t j = 0; j < nb; j++) L.b.push_back(col + na + t * nb + j);
-            uint32_t a_filter = col + na + nt * nb;
-            for (uint32_t t = 0; t < nt; t++) L.bf.push_back(a_filter + 1 + t);
-            uint32_t a_inv = a_filter + nt + 1;
-            for (uint32_t t = 0; t < nt; t++) L.bi.push_back(a_inv + 1 + t);
-            for (uint32_t t = 0; t < nt; t++) L.occ.push_back(a_inv + nt + 1 + t);
-            lsp_lookup_air_cfg c = {na, L.a.data(), nt, nb, L.b.data(), a_filter, L.bf.data(), a_inv, L.bi.data(), L.occ.data(),
-                                    a_inv + 2 * nt + 1};
-            lcfg.push_back(c);
-            printf("  lookup %s: %zu rows, %u columns, %u tables\n", name, rows, na, nt);
-            col += na + nt * (nb + 3) + 3;
-            if (height && rows != height) {
-                fprintf(stderr, "all sub-traces must have one height (%zu != %zu)\n", rows, height);
+        size_t height = 0, li = 0, pi = 0;
+        for (const SubTrace& st : subs) {
+            if (height && st.rows != height) {
+                fprintf(stderr, "all sub-traces must have one height (%zu != %zu)\n", st.rows, height);
                 return 1;
             }
-            height = rows;
-        }
-        for (size_t k = 0; k < perms.size(); k++) {
-            clk::time_point t0 = clk::now();
-            MappedFile blob(perms[k]);
-            t_read += ms_since(t0);
-            cbor_bytes += blob.size();
-            size_t rows = 0;
-            uint32_t nc = 0;
-            char name[128];
-            t0 = clk::now();
-            uint8_t* be_raw = nullptr;
-            CHECK(ctx, lsp_cbor_permutation_read(blob.data(), blob.size(), &rows, &nc, name, sizeof name, &be_raw));
-            HostBytes be(be_raw);
-            t_cbor += ms_since(t0);
-            lsp_mat* m = nullptr;
-            t0 = clk::now();
-            CHECK(ctx, lsp_permutation_trace_be(ctx, be.data(), rows, nc, publics, &m));
-            CHECK(ctx, lsp_ctx_sync(ctx));
-            t_witness += ms_since(t0);
-            parts.push_back(m);
-            for (uint32_t j = 0; j < nc; j++) {  // trace/src/permutation.rs:84-92, shifted
-                pa[k].push_back(col + j);
-                pb[k].push_back(col + nc + j);
+            height = st.rows;
+            if (st.lookup) {
+                const uint32_t na = st.na, nt = st.nt, nb = st.nb;
+                LookupIds& L = lids[li++];  // get_air_lookup_config (trace/src/lookup.rs:178-214), shifted by `col`
+                for (uint32_t j = 0; j < na; j++) L.a.push_back(col + j);
+                for (uint32_t t = 0; t < nt; t++)
+                    for (uint32_t j = 0; j < nb; j++) L.b.push_back(col + na + t * nb + j);
+                uint32_t a_filter = col + na + nt * nb;
+                for (uint32_t t = 0; t < nt; t++) L.bf.push_back(a_filter + 1 + t);
+                uint32_t a_inv = a_filter + nt + 1;
+                for (uint32_t t = 0; t < nt; t++) L.bi.push_back(a_inv + 1 + t);
+                for (uint32_t t = 0; t < nt; t++) L.occ.push_back(a_inv + nt + 1 + t);
+                lsp_lookup_air_cfg c = {na, L.a.data(), nt, nb, L.b.data(), a_filter, L.bf.data(), a_inv, L.bi.data(), L.occ.data(),
+                                        a_inv + 2 * nt + 1};
+                lcfg.push_back(c);
+                printf("  lookup %s: %zu rows, %u columns, %u tables\n", st.name.c_str(), st.rows, na, nt);
+                col += na + nt * (nb + 3) + 3;
+            } else {
+                const uint32_t nc = st.na;
+                for (uint32_t j = 0; j < nc; j++) {  // trace/src/permutation.rs:84-92, shifted
+                    pa[pi].push_back(col + j);
+                    pb[pi].push_back(col + nc + j);
+                }
+                lsp_perm_air_cfg c = {nc, pa[pi].data(), pb[pi].data(), col + 2 * nc, col + 2 * nc + 1};
+                pcfg.push_back(c);
+                pi++;
+                printf("  permutation %s: %zu rows, %u + %u columns\n", st.name.c_str(), st.rows, nc, nc);
+                col += 2 * nc + 2;
             }
-            lsp_perm_air_cfg c = {nc, pa[k].data(), pb[k].data(), col + 2 * nc, col + 2 * nc + 1};
-            pcfg.push_back(c);
-            printf("  permutation %s: %zu rows, %u + %u columns\n", name, rows, nc, nc);
-            col += 2 * nc + 2;
-            if (height && rows != height) {
-                fprintf(stderr, "all sub-traces must have one height (%zu != %zu)\n", rows, height);
-                return 1;
-            }
-            height = rows;
         }
-        lsp_mat* trace = nullptr;
-        const clk::time_point t_cat0 = clk::now();
-        CHECK(ctx, lsp_mat_hconcat(ctx, parts.data(), int(parts.size()), &trace));
-        CHECK(ctx, lsp_ctx_sync(ctx));
-        const double t_cat = ms_since(t_cat0), t_gen = ms_since(t_gen0);
+
+        // ---- get_trace + push_traces on every GPU (each rank needs the whole trace to interpolate its columns)
+        const clk::time_point t_wit0 = clk::now();
+        on_all_ranks(ranks, [&](Rank& r, int) {
+            std::vector<lsp_mat*> parts;
+            for (const SubTrace& st : subs) {
+                lsp_mat* m = nullptr;
+                if (st.lookup)
+                    CHECK(r.ctx, lsp_lookup_trace_be(r.ctx, st.be, st.rows, st.na, st.nt, st.nb, publics, &m));
+                else
+                    CHECK(r.ctx, lsp_permutation_trace_be(r.ctx, st.be, st.rows, st.na, publics, &m));
+                parts.push_back(m);
+            }
+            CHECK(r.ctx, lsp_mat_hconcat(r.ctx, parts.data(), int(parts.size()), &r.trace));
+            CHECK(r.ctx, lsp_ctx_sync(r.ctx));
+            for (lsp_mat* m : parts) lsp_mat_free(r.ctx, m);
+        });
+        const double t_witness = ms_since(t_wit0), t_gen = ms_since(t_gen0);
         printf("trace generation [ %.3f ms ]: map files %.3f ms, CBOR parse %.3f ms (%.1f MB, %.0f MB/s), "
-               "witness on the device (upload included) %.3f ms, push_traces %.3f ms, other %.3f ms\n",
-               t_gen, t_read, t_cbor, cbor_bytes / 1e6, t_cbor > 0 ? cbor_bytes / 1e3 / t_cbor : 0.0, t_witness, t_cat,
-               t_gen - t_read - t_cbor - t_witness - t_cat);
+               "witness on the device%s (upload and push_traces included) %.3f ms, other %.3f ms\n",
+               t_gen, t_read, t_cbor, cbor_bytes / 1e6, t_cbor > 0 ? cbor_bytes / 1e3 / t_cbor : 0.0, gpus > 1 ? "s" : "", t_witness,
+               t_gen - t_read - t_cbor - t_witness);
         printf("Creating LineaAir...  (%zu rows x %u columns)\n", height, col);
 
         // ---- prove (main.rs:80-86)
@@ -280,18 +327,34 @@ int main(int argc, char** argv) {
         while ((size_t(1) << log_n) < height) log_n++;
         int log_q = lsp_air_log_quotient_degree(int(lcfg.size()), int(pcfg.size()));
         size_t words = lsp_proof_words(uint32_t(log_n), col, uint32_t(log_q), &fri);
-        std::vector<uint64_t> proof(words);
+        std::vector<std::vector<uint64_t>> proofs(ranks.size(), std::vector<uint64_t>(words));
+        std::vector<uint64_t>& proof = proofs[0];
         float tm[8] = {0};
-        printf("Proving...\n");
-        CHECK(ctx, lsp_prove_air_dev(ctx, &fri, trace, lcfg.data(), int(lcfg.size()), pcfg.data(), int(pcfg.size()), publics, proof.data(),
-                                     words, tm));
+        printf("Proving...%s\n", gpus > 1 ? "  (one proof sharded by LDE row ranges)" : "");
+        const clk::time_point t_prove0 = clk::now();
+        on_all_ranks(ranks, [&](Rank& r, int k) {
+            float tmk[8] = {0};
+            if (gpus == 1)
+                CHECK(r.ctx, lsp_prove_air_dev(r.ctx, &fri, r.trace, lcfg.data(), int(lcfg.size()), pcfg.data(), int(pcfg.size()), publics,
+                                               proofs[size_t(k)].data(), words, tmk));
+            else
+                CHECK(r.ctx, lsp_prove_air_sharded_dev(r.comm, &fri, r.trace, lcfg.data(), int(lcfg.size()), pcfg.data(), int(pcfg.size()),
+                                                       publics, proofs[size_t(k)].data(), words, tmk));
+            if (k == 0) memcpy(tm, tmk, sizeof tm);
+        });
+        const double t_prove_wall = ms_since(t_prove0);
+        for (size_t k = 1; k < proofs.size(); k++)
+            if (proofs[k] != proof) {
+                fprintf(stderr, "rank %zu holds a different proof than rank 0\n", k);
+                return 1;
+            }
         const char* spans[8] = {"commit to trace data: coset_lde_batch", "commit to trace data: merkle tree",
                                 "compute quotient polynomial",           "commit to quotient poly chunks",
                                 "open: opened values + reduced openings", "FRI prover: commit phase",
                                 "FRI prover: grind + query phase",        "proof copy to host"};
         float total = 0;
         for (int i = 0; i < 8; i++) total += tm[i];
-        printf("prove [ %.3f ms ]\n", total);
+        printf("prove [ %.3f ms device, %.3f ms wall%s ]\n", total, t_prove_wall, gpus > 1 ? ", all ranks" : "");
         for (int i = 0; i < 8; i++) printf("  %-44s [ %8.3f ms | %5.1f%% ]\n", spans[i], tm[i], 100.0 * tm[i] / total);
         printf("trace commitment   (Montgomery limbs): %016llx%016llx%016llx%016llx\n", (unsigned long long)proof[3],
                (unsigned long long)proof[2], (unsigned long long)proof[1], (unsigned long long)proof[0]);
@@ -306,6 +369,10 @@ int main(int argc, char** argv) {
                                      proof.data(), words, &verify_ms);
         if (verdict < 0) CHECK(ctx, verdict);
         printf("verify [ %.3f ms ]: %s\n", verify_ms, verdict == 0 ? "proof accepted" : "PROOF REJECTED");
+        for (Rank& r : ranks) {
+            lsp_mat_free(r.ctx, r.trace);
+            r.trace = nullptr;
+        }
         if (verdict != 0) {
             fprintf(stderr, "verification failed: LSP_VERIFY code %d\n", verdict);
             return 2;
@@ -315,8 +382,6 @@ int main(int argc, char** argv) {
             f.write(reinterpret_cast<const char*>(proof.data()), std::streamsize(words * 8));
             printf("proof written to %s (layout in DESIGN.md section 7)\n", out_path.c_str());
         }
-        lsp_mat_free(ctx, trace);
-        for (lsp_mat* m : parts) lsp_mat_free(ctx, m);
         return 0;
     };
     int status = 0;
@@ -324,6 +389,9 @@ int main(int argc, char** argv) {
         if (repeat > 1) printf("---- pass %d of %d ----\n", rep + 1, repeat);
         status = run_once();
     }
-    lsp_ctx_destroy(ctx);
+    on_all_ranks(ranks, [&](Rank& r, int) {
+        if (r.comm) lsp_comm_destroy(r.comm);
+        lsp_ctx_destroy(r.ctx);
+    });
     return status;
 }

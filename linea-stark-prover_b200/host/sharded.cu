@@ -40,11 +40,8 @@ struct NcclApi {
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
-NcclApi* nccl_api() {
+NcclApi* load_nccl() {
     static NcclApi api;
-    static bool tried = false;
-    if (tried) return api.lib ? &api : nullptr;
-    tried = true;
     // RTLD_NOLOAD first: reuse the copy torch.distributed already mapped, if any
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
@@ -63,6 +60,13 @@ NcclApi* nccl_api() {
         return nullptr;
     }
     return &api;
+}
+
+// Loaded once; a function-local static is initialised under a lock, so the host threads of a
+// one-process-many-GPUs driver (lsp_prove --gpus N) may all arrive here at once.
+NcclApi* nccl_api() {
+    static NcclApi* const api = load_nccl();
+    return api;
 }
 
 }  // namespace

@@ -60,3 +60,33 @@ def test_driver_fails_loudly_on_bad_input(tmp_path):
     (tmp_path / "junk.bin").write_bytes(b"\x00\x01\x02")
     r = subprocess.run([str(EXE), "--permutation", str(tmp_path / "junk.bin")], capture_output=True, text=True, timeout=120)
     assert r.returncode != 0 and "lsp_cbor_permutation_read" in r.stderr
+
+
+def test_driver_shards_one_proof_over_two_gpus(tmp_path):
+    """`lsp_prove --gpus 2`: one host thread and one context per GPU, NCCL between them; the proof must be the
+    single-GPU proof byte for byte (and the binary itself verifies it on the device before writing it)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    n, seed = 256, 777
+    lk = OT.synthetic_lookup_input(3, 2, 1, n, disabled_every=5)
+    pa, pb = OT.synthetic_permutation_input(4, 2, n)
+    (tmp_path / "lookup_0.bin").write_bytes(OT.encode_raw_lookup_trace(*lk, "lookup_0"))
+    (tmp_path / "perm_0.bin").write_bytes(OT.encode_raw_permutation_trace(pa, pb, "perm_0"))
+    outs = []
+    for gpus in (1, 2):
+        out = tmp_path / f"proof_{gpus}.bin"
+        r = subprocess.run([str(EXE), "--lookup", str(tmp_path / "lookup_0.bin"), "--permutation", str(tmp_path / "perm_0.bin"),
+                            "--seed", str(seed), "--queries", "12", "--gpus", str(gpus), "--out", str(out)],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "proof accepted" in r.stdout
+        outs.append(out.read_bytes())
+    assert outs[0] == outs[1] and len(outs[0]) > 0
+
+
+def test_driver_rejects_bad_gpu_counts(tmp_path):
+    (tmp_path / "p.bin").write_bytes(OT.encode_raw_permutation_trace(*OT.synthetic_permutation_input(1, 1, 8), "p"))
+    for gpus in ("3", "16", "0"):
+        r = subprocess.run([str(EXE), "--permutation", str(tmp_path / "p.bin"), "--gpus", gpus], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 2 and "--gpus" in r.stderr
