@@ -258,7 +258,8 @@ int lsp_prove_air_dev(lsp_ctx* ctx, const lsp_fri_config* fri, const lsp_mat* tr
  * and the out-of-domain identity  sum_i zp_i(zeta) chunk_i(zeta) = constraints(zeta) / Z_H(zeta).
  * `proof` is the flat array lsp_prove_* wrote (host memory); `log_n` is the proof's `degree_bits`,
  * `width` the AIR width.  `device_ms_out` (optional) receives the CUDA-event time of the whole check,
- * upload included.  A proof with zero commit-phase rounds (log_final_poly_len == log_n) is rejected
+ * upload included.  Every element must be canonical (< r), as the reference's deserialiser requires: a proof carrying
+ * x + r in place of x is INVALID_PROOF_SHAPE.  A proof with zero commit-phase rounds (log_final_poly_len == log_n) is rejected
  * with FINAL_POLY_MISMATCH, as the pinned verifier does (the reduced opening only enters inside a round). */
 int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t log_n, size_t width,
                    const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,

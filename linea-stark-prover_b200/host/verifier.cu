@@ -70,6 +70,17 @@ __global__ void __launch_bounds__(32) k_merkle_paths(const __grid_constant__ P2P
     }
 }
 
+// Deserialisation check: every field element of the proof must be the canonical representative (< r), as
+// `Bls12_377Fr`'s deserialiser demands; the per-query index words are small integers and pass trivially.
+__global__ void __launch_bounds__(128) k_verify_canonical(const Fr* __restrict__ proof, size_t n_elems, int* __restrict__ bad) {
+    const uint32_t p[8] = {LSP_P0, LSP_P1, LSP_P2, LSP_P3, LSP_P4, LSP_P5, LSP_P6, LSP_P7};
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n_elems; i += size_t(gridDim.x) * blockDim.x) {
+        Fr v = fr_load(proof + i);
+        uint32_t t[8];
+        if (u256_sub(t, v.l, p) == 0) atomicExch(bad, 1);   // no borrow: v >= r
+    }
+}
+
 struct VerifyArgs {
     const Fr *proof, *p_local, *p_next, *p_chunks, *p_commits, *p_final, *p_queries;
     const Fr *publics, *scal, *betas;
@@ -283,7 +294,7 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     LSP_TRY(S.get((void**)&betas, size_t(n_rounds ? n_rounds : 1) * 32));
     LSP_TRY(S.get((void**)&evbuf, size_t(nq) * (n_rounds ? n_rounds : 1) * 2 * 32));
     const size_t st_per = size_t(ST_ROUND + n_rounds);
-    const size_t n_status = 2 + size_t(nq) * st_per;  // [pow_low, ood_bad, per-query blocks]
+    const size_t n_status = 3 + size_t(nq) * st_per;  // [pow_low, ood_bad, non-canonical element, per-query blocks]
     if ((n_status + 1) * 4 > ctx->pinned_bytes) return set_err(ctx, LSP_ERR_PARAM, "too many queries x rounds for the status block");
     int* status = nullptr;
     uint32_t* idx = nullptr;
@@ -321,7 +332,7 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     A.n_queries = nq;
     A.per_query = (proof_elems - size_t(A.p_queries - proof)) / size_t(nq);
     A.ev = evbuf;
-    A.status = status + 2;
+    A.status = status + 3;
     A.ood_bad = status + 1;
     A.cfg = cfg_dev;
 
@@ -343,6 +354,8 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     T.betas = betas;
     T.pow_low = reinterpret_cast<uint32_t*>(status);
     T.idx = idx;
+    LSP_CUDA(ctx, cudaMemsetAsync(status + 2, 0, 4, ctx->stream));
+    LSP_LAUNCH(ctx, k_verify_canonical, grid_for(ctx, proof_elems, 128), 128, 0, (const Fr*)proof, proof_elems, status + 2);
     LSP_TRY(verify_transcript(ctx, ch, T));
     LSP_LAUNCH(ctx, k_verify_fold, unsigned((nq + 31) / 32), 32, 0, A);
     LSP_LAUNCH(ctx, k_verify_path_jobs, unsigned((n_jobs + 127) / 128), 128, 0, A, jobs);
@@ -357,9 +370,10 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     const int* h = static_cast<const int*>(ctx->pinned);
     if (h[n_status]) return set_err(ctx, LSP_ERR_STATE, "challenger input buffer overflow");
     // first failing check, in the order the reference verifier meets them
+    if (h[2]) return LSP_VERIFY_INVALID_PROOF_SHAPE;   // an element >= r: the proof would not have deserialised
     if (h[0] != 0) return LSP_VERIFY_INVALID_POW_WITNESS;
     for (int qi = 0; qi < nq; qi++) {
-        const int* st = h + 2 + size_t(qi) * st_per;
+        const int* st = h + 3 + size_t(qi) * st_per;
         if (st[ST_INDEX]) return LSP_VERIFY_INVALID_PROOF_SHAPE;
         if (st[ST_TRACE]) return LSP_VERIFY_TRACE_OPENING;
         if (st[ST_QUOT]) return LSP_VERIFY_QUOTIENT_OPENING;

@@ -593,6 +593,8 @@ int lsp_oracle_verify(const fri_cfg* fri, uint32_t log_n, size_t width, const ai
     const int n_rounds = (int)log_n - (int)fri->log_final_poly_len, log_f = log_b + (int)fri->log_final_poly_len;
     if (proof_words != lsp_oracle_proof_words(log_n, (uint32_t)W, (uint32_t)log_q, fri)) return 1;
     const fr* proof = (const fr*)proof_in;
+    for (size_t i = 0; i < proof_words / 4; i++)      /* deserialisation: every element must be canonical (< r) */
+        if (geq_p(proof[i].l)) return 1;
     const fr *p_local = proof + 2, *p_next = p_local + W, *p_chunks = p_next + W, *p_commits = p_chunks + q,
              *p_final = p_commits + n_rounds, *p_pow = p_final + ((size_t)1 << log_f), *p_queries = p_pow + 1;
     fr pub[2]; memcpy(pub, publics, 64);

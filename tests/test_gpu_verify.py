@@ -228,3 +228,26 @@ def test_mmcs_verify_batch(pkg, gctx, p2params, log_h, widths):
                 assert not mm.verify_batch(root, log_h, idx, rows, bad_proof)
             assert not mm.verify_batch(root, log_h, idx ^ 1, rows, proof)
     tree.free()
+
+
+def test_non_canonical_elements_do_not_deserialise(pkg, gctx, p2params):
+    """x and x + r are the same field element but not the same encoding: `Bls12_377Fr`'s deserialiser refuses the second,
+    so both verifiers report a malformed proof wherever it appears -- even in a slot where the arithmetic would not care."""
+    from oracle import cport
+    cport.set_poseidon2(p2params)
+    log_n, fri_kw = 5, dict(log_blowup=2, log_final_poly_len=0, num_queries=5, proof_of_work_bits=0)
+    cfgs, g, gproof, publics, pub = _perm_case(pkg, gctx, cport, log_n, [2], fri_kw, 2718)
+    reg, _ = _regions(log_n, gproof.width, 2, fri_kw)
+    vals = pkg.from_mont_array(gproof.words.reshape(-1, 4))       # canonical integers of the Montgomery residues' VALUES
+    for name in ("trace_local", "chunks", "final_poly", "q0.trace_row", "q4.quot_path", "q2.r1.sibling"):
+        e = reg[name][0]
+        limbs = gproof.words.reshape(-1, 4)[e]
+        stored = sum(int(limbs[k]) << (64 * k) for k in range(4))          # the Montgomery representative as stored
+        if stored + F.R_MOD >= 1 << 256:
+            continue
+        bad = gproof.words.copy()
+        for k in range(4):
+            bad[4 * e + k] = np.uint64(((stored + F.R_MOD) >> (64 * k)) & (2 ** 64 - 1))
+        assert cport.verify_limbs(OS.FriConfig(**fri_kw), log_n, gproof.width, cfgs, pub, bad) == 1, name
+        assert pkg.verify_code(gctx, pkg.FriConfig(**fri_kw), g, bad, publics, log_n, gproof.width) == 1, name
+    del vals
