@@ -424,8 +424,9 @@ def pcs_verify(p, fri: FriConfig, rounds, proof, challenger):
                 raise VerificationError("CommitPhaseMmcsError")
             dom_index >>= 1
             folded_eval = fold_row(dom_index, log_fh, beta, evals[0], evals[1])
-        if ro_i != len(ro_list):
-            raise VerificationError("InvalidProofShape")
+        # Upstream only `debug_assert!`s that every reduced opening was consumed; the reference runs `--release`
+        # (README.md:6), where a proof with zero commit-phase rounds (log_final_poly_len == degree_bits) therefore
+        # reaches the final-polynomial check with folded_eval = 0 and fails THERE.  Mirror the release behaviour.
         x = pow(two_adic_generator(log_global_max), reverse_bits_len(dom_index, log_global_max), R_MOD)
         ev, xp = 0, 1
         for c in proof["final_poly"]:

@@ -116,8 +116,8 @@ def test_random_shapes_against_the_c_port(pkg, gctx, p2params):
         gproof = pkg.prove(gctx, pkg.FriConfig(**fri_kw), g, (tr, n, w), pkg.from_mont_array(pub))
         assert np.array_equal(cwords, gproof.words), (log_n, c, fri_kw)
         # Zero commit-phase rounds (final polynomial as long as the trace): the prover side is well defined and must
-        # still match, but the restated verifier -- like the pinned Plonky3 one it follows, whose query loop only adds the
-        # reduced opening inside a folding round -- rejects such a proof (shape error, code 5). Keep that pinned.
+        # still match, but the restated verifiers -- like the pinned Plonky3 one they follow, whose query loop only adds
+        # the reduced opening inside a folding round -- reject such a proof (FinalPolyMismatch, code 5).  Keep that pinned.
         want = 5 if log_final == log_n else 0
         assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, gproof.words) == want, (log_n, c, fri_kw)
         assert pkg.verify_code(gctx, pkg.FriConfig(**fri_kw), g, gproof, pkg.from_mont_array(pub)) == want, (log_n, c, fri_kw)

@@ -120,3 +120,23 @@ def test_c_verifier_names_the_same_failing_check_as_the_python_verifier(p2params
     name, code = both(good, swapped)
     assert (name, code) == ("OodEvaluationMismatch", 7)
     assert {"InputError(MerkleRootMismatch)", "CommitPhaseMmcsError"} <= seen
+
+
+def test_zero_round_fri_is_rejected_at_the_final_polynomial_by_both_verifiers(p2params):
+    """log_final_poly_len == log2(height): the provers agree, and both verifiers -- like the pinned Plonky3 one in a
+    release build -- never add the reduced opening (that happens inside a folding round) and report FinalPolyMismatch."""
+    cport.set_poseidon2(p2params)
+    for log_n, log_blowup in ((1, 1), (3, 2)):
+        fri = OS.FriConfig(log_blowup=log_blowup, log_final_poly_len=log_n, num_queries=4, proof_of_work_bits=0)
+        rng = F.SplitMix64(50 + log_n)
+        alpha, delta = rng.next_fr(), rng.next_fr()
+        cfgs, trace = OT.build_trace([OT.synthetic_permutation_input(3, 2, 1 << log_n)], alpha, delta)
+        dbg = {}
+        proof = OS.prove(p2params, fri, cfgs, trace, [alpha, delta], dbg)
+        words = cport.prove(fri, cfgs, trace, [alpha, delta])
+        assert np.array_equal(words, flat_from_dict(proof, dbg["query_indices"]))
+        assert proof["opening_proof"]["commit_phase_commits"] == []
+        with pytest.raises(OS.VerificationError, match="FinalPolyMismatch"):
+            OS.verify(p2params, fri, cfgs, proof, [alpha, delta])
+        pub = np.array([F.to_mont_limbs(alpha), F.to_mont_limbs(delta)], dtype=np.uint64)
+        assert cport.verify_limbs(fri, log_n, OA.air_width(cfgs), cfgs, pub, words) == 5
