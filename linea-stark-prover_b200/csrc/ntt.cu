@@ -190,26 +190,6 @@ static int launch_pass(lsp_ctx* ctx, bool dif, const NttPass& P, size_t width, i
     return LSP_OK;
 }
 
-static Fr host_pow2_inverse(int k) {
-    // 2^-k in Montgomery form: halve (R mod r) k times on the host (4 x u64 arithmetic)
-    uint64_t v[4] = {0x7d1c7ffffffffff3ull, 0x7257f50f6ffffff2ull, 0x16d81575512c0feeull, 0x0d4bda322bbb9a9dull};
-    static const uint64_t Pm[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
-    for (int i = 0; i < k; i++) {
-        if (v[0] & 1) {
-            unsigned __int128 c = 0;
-            for (int j = 0; j < 4; j++) {
-                c += (unsigned __int128)v[j] + Pm[j];
-                v[j] = (uint64_t)c;
-                c >>= 64;
-            }
-        }
-        for (int j = 0; j < 3; j++) v[j] = (v[j] >> 1) | (v[j + 1] << 63);
-        v[3] >>= 1;
-    }
-    Fr r;
-    memcpy(r.l, v, 32);
-    return r;
-}
 
 // Coefficients (natural order, true scale) of every column of `in` (N x W, column-major).
 int interpolate_columns(lsp_ctx* ctx, const Fr* in, size_t n, size_t width, Fr* coeffs) {

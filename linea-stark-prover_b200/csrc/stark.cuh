@@ -33,6 +33,28 @@ __device__ __forceinline__ Fr fr_two_adic_generator(int bits) {
 
 __device__ __forceinline__ uint32_t bitrev32(uint32_t x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
 
+// 2^-k in Montgomery form, on the host: halve (R mod r) k times with 4 x u64 arithmetic.  (1/N of the inverse
+// transform, 1/F of the final-polynomial interpolation: kernel arguments, never read back from the device.)
+inline Fr host_pow2_inverse(int k) {
+    uint64_t v[4] = {0x7d1c7ffffffffff3ull, 0x7257f50f6ffffff2ull, 0x16d81575512c0feeull, 0x0d4bda322bbb9a9dull};
+    static const uint64_t Pm[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
+    for (int i = 0; i < k; i++) {
+        if (v[0] & 1) {
+            unsigned __int128 c = 0;
+            for (int j = 0; j < 4; j++) {
+                c += (unsigned __int128)v[j] + Pm[j];
+                v[j] = (uint64_t)c;
+                c >>= 64;
+            }
+        }
+        for (int j = 0; j < 3; j++) v[j] = (v[j] >> 1) | (v[j + 1] << 63);
+        v[3] >>= 1;
+    }
+    Fr r;
+    memcpy(r.l, v, 32);
+    return r;
+}
+
 // ---- ntt.cu ----------------------------------------------------------------
 int interpolate_columns(lsp_ctx* ctx, const Fr* in, size_t n, size_t width, Fr* coeffs);
 // shift_dev: device pointer to the coset shift (so that data-dependent shifts never visit the host)

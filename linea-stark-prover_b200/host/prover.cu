@@ -22,6 +22,7 @@
 //   per query: 1 index | W trace row, log2 L siblings | q chunk row, log2 L siblings |
 //              per round r: sibling value, (log2 L - 1 - r) siblings
 #include "../csrc/stark.cuh"
+#include "prove_kernels.cuh"
 
 using namespace lsp;
 
@@ -78,24 +79,6 @@ __global__ void __launch_bounds__(128) k_query_gather(const __grid_constant__ Qu
     }
 }
 
-// Scalars the reduced-opening kernel needs, from the opened values:
-//   s[0] = sum_i a^i y_zeta[i]   s[1] = sum_i a^i y_zeta'[i]   s[2] = sum_c a^c yq[c]
-//   s[3] = a^W                   s[4] = a^(2W)
-__global__ void k_open_scalars(const Fr* __restrict__ alpha, const Fr* __restrict__ y_zeta, const Fr* __restrict__ y_next,
-                               const Fr* __restrict__ yq, int width, int q, Fr* __restrict__ s) {
-    Fr a = fr_load(alpha);
-    auto horner = [&](const Fr* y, int n) {
-        Fr acc = fr_load(y + n - 1);
-        for (int i = n - 2; i >= 0; i--) acc = fr_add(fr_mul(acc, a), fr_load(y + i));
-        return acc;
-    };
-    fr_store(s + 0, horner(y_zeta, width));
-    fr_store(s + 1, horner(y_next, width));
-    fr_store(s + 2, horner(yq, q));
-    Fr aw = fr_pow_u32(a, uint32_t(width));
-    fr_store(s + 3, aw);
-    fr_store(s + 4, fr_sqr(aw));
-}
 
 // zeta' = zeta * w_N ; chunk points z_c = zeta / (g * w_{Nq}^c)
 __global__ void k_open_points(const Fr* __restrict__ zeta, int log_n, int log_q, Fr* __restrict__ zeta_next, Fr* __restrict__ chunk_pts) {
@@ -146,25 +129,7 @@ __global__ void __launch_bounds__(128) k_reduce_openings(const __grid_constant__
     }
 }
 
-// final_poly = idft(bit_reverse(folded)); F <= 1024 values, one thread per coefficient.
-__global__ void k_final_poly(const Fr* __restrict__ folded, int log_f, Fr scale /* 1/F */, Fr* __restrict__ out) {
-    int k = threadIdx.x;
-    int f = 1 << log_f;
-    if (k >= f) return;
-    Fr w = fr_two_adic_generator(log_f);
-    Fr wk = fr_pow_u32(w, uint32_t((f - k) & (f - 1)));  // w^-k
-    Fr acc = fr_zero(), wp = fr_one();
-    for (int j = 0; j < f; j++) {
-        acc = fr_add(acc, fr_mul(fr_load(folded + bitrev32(uint32_t(j), log_f)), wp));
-        wp = fr_mul(wp, wk);
-    }
-    fr_store(out + k, fr_mul(acc, scale));
-}
 
-__global__ void k_make_cols(const Fr* base, size_t stride, int n, const Fr** out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n) out[c] = base + size_t(c) * stride;
-}
 // round r: input vector at folded_all + (2L - 2L>>r), digests at fri_digests + (2L - 2L>>r) - r
 __global__ void k_make_rounds(const Fr* folded_all, const Fr* fri_digests, int log_l, int n_rounds, FriRoundDev* out) {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -176,31 +141,7 @@ __global__ void k_make_rounds(const Fr* folded_all, const Fr* fri_digests, int l
     out[r].log_h = uint32_t(log_l - 1 - r);
 }
 
-__global__ void k_set_small(Fr* dst, uint32_t v) {  // dst = Fr::from_canonical(v)
-    Fr x = fr_zero();
-    x.l[0] = v;
-    fr_store(dst, fr_mul(x, fr_const(FR_R2)));
-}
 
-Fr host_pow2_inverse(int k) {
-    uint64_t v[4] = {0x7d1c7ffffffffff3ull, 0x7257f50f6ffffff2ull, 0x16d81575512c0feeull, 0x0d4bda322bbb9a9dull};
-    static const uint64_t Pm[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
-    for (int i = 0; i < k; i++) {
-        if (v[0] & 1) {
-            unsigned __int128 c = 0;
-            for (int j = 0; j < 4; j++) {
-                c += (unsigned __int128)v[j] + Pm[j];
-                v[j] = (uint64_t)c;
-                c >>= 64;
-            }
-        }
-        for (int j = 0; j < 3; j++) v[j] = (v[j] >> 1) | (v[j + 1] << 63);
-        v[3] >>= 1;
-    }
-    Fr r;
-    memcpy(r.l, v, 32);
-    return r;
-}
 
 int max_constraint_log_quotient(int n_lookups, int /*n_perms*/) {
     // `get_log_quotient_degree`, log2_ceil(max degree - 1):

@@ -24,6 +24,7 @@
 #include <nccl.h>
 
 #include "../csrc/stark.cuh"
+#include "prove_kernels.cuh"
 
 using namespace lsp;
 
@@ -144,15 +145,6 @@ int coll_allreduce_sum(lsp_comm* cm, const std::vector<int>& ranks, const std::v
 }
 
 // ---- device helpers --------------------------------------------------------------------------
-__global__ void k_make_cols_s(const Fr* base, size_t stride, int n, const Fr** out) {
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < n) out[c] = base + size_t(c) * stride;
-}
-__global__ void k_set_small_s(Fr* dst, uint32_t v) {
-    Fr x = fr_zero();
-    x.l[0] = v;
-    fr_store(dst, fr_mul(x, fr_const(FR_R2)));
-}
 __global__ void k_chunk_consts(const Fr* __restrict__ zeta, int log_n, int log_q, Fr* __restrict__ shifts, Fr* __restrict__ zeta_next,
                                Fr* __restrict__ chunk_pts) {
     int c = threadIdx.x;
@@ -164,21 +156,6 @@ __global__ void k_chunk_consts(const Fr* __restrict__ zeta, int log_n, int log_q
         if (zeta) fr_store(chunk_pts + c, fr_mul(fr_mul(fr_load(zeta), fr_const(FR_GEN_INV)), wi));
     }
     if (c == 0 && zeta) fr_store(zeta_next, fr_mul(fr_load(zeta), fr_two_adic_generator(log_n)));
-}
-__global__ void k_open_scalars_s(const Fr* __restrict__ alpha, const Fr* __restrict__ y_zeta, const Fr* __restrict__ y_next,
-                                 const Fr* __restrict__ yq, int width, int q, Fr* __restrict__ s) {
-    Fr a = fr_load(alpha);
-    auto horner = [&](const Fr* y, int n) {
-        Fr acc = fr_load(y + n - 1);
-        for (int i = n - 2; i >= 0; i--) acc = fr_add(fr_mul(acc, a), fr_load(y + i));
-        return acc;
-    };
-    fr_store(s + 0, horner(y_zeta, width));
-    fr_store(s + 1, horner(y_next, width));
-    fr_store(s + 2, horner(yq, q));
-    Fr aw = fr_pow_u32(a, uint32_t(width));
-    fr_store(s + 3, aw);
-    fr_store(s + 4, fr_sqr(aw));
 }
 struct ReduceArgsS {
     const Fr* trace_lde; size_t rows; int width;
@@ -198,38 +175,6 @@ __global__ void __launch_bounds__(128) k_reduce_openings_s(const __grid_constant
         Fr t1 = fr_mul(aw, fr_sub(rt, ytn));
         fr_store(A.out + p, fr_add(fr_mul(t0, fr_load_nc(A.e_zeta + p)), fr_mul(t1, fr_load_nc(A.e_next + p))));
     }
-}
-__global__ void k_final_poly_s(const Fr* __restrict__ folded, int log_f, Fr scale, Fr* __restrict__ out) {
-    int k = threadIdx.x;
-    int f = 1 << log_f;
-    if (k >= f) return;
-    Fr w = fr_two_adic_generator(log_f);
-    Fr wk = fr_pow_u32(w, uint32_t((f - k) & (f - 1)));
-    Fr acc = fr_zero(), wp = fr_one();
-    for (int j = 0; j < f; j++) {
-        acc = fr_add(acc, fr_mul(fr_load(folded + bitrev32(uint32_t(j), log_f)), wp));
-        wp = fr_mul(wp, wk);
-    }
-    fr_store(out + k, fr_mul(acc, scale));
-}
-Fr pow2_inverse(int k) {
-    uint64_t v[4] = {0x7d1c7ffffffffff3ull, 0x7257f50f6ffffff2ull, 0x16d81575512c0feeull, 0x0d4bda322bbb9a9dull};
-    static const uint64_t Pm[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
-    for (int i = 0; i < k; i++) {
-        if (v[0] & 1) {
-            unsigned __int128 c = 0;
-            for (int j = 0; j < 4; j++) {
-                c += (unsigned __int128)v[j] + Pm[j];
-                v[j] = (uint64_t)c;
-                c >>= 64;
-            }
-        }
-        for (int j = 0; j < 3; j++) v[j] = (v[j] >> 1) | (v[j + 1] << 63);
-        v[3] >>= 1;
-    }
-    Fr r;
-    memcpy(r.l, v, 32);
-    return r;
 }
 
 // A Merkle tree whose leaves are split over G ranks: local layers + replicated top.
@@ -506,8 +451,8 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         R.rank = ranks[i];
         LSP_TRY(P.get(&R.sc, S_COUNT * 32));
         LSP_CUDA(ctx, cudaMemcpyAsync(R.sc + S_PUB0, publics, 64, cudaMemcpyHostToDevice, ctx->stream));
-        LSP_LAUNCH(ctx, k_set_small_s, 1, 1, 0, R.sc + S_LOGN, uint32_t(log_n));
-        LSP_LAUNCH(ctx, k_set_small_s, 1, 1, 0, R.sc + S_GEN, 22u);
+        LSP_LAUNCH(ctx, k_set_small, 1, 1, 0, R.sc + S_LOGN, uint32_t(log_n));
+        LSP_LAUNCH(ctx, k_set_small, 1, 1, 0, R.sc + S_GEN, 22u);
         LSP_TRY(P.get(&R.ch, sizeof(DevChallenger)));
         LSP_TRY(challenger_init(ctx, R.ch));
         LSP_TRY(P.get(&R.proof, proof_elems * 32));
@@ -525,7 +470,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         std::vector<void*> recv(H);
         for (size_t i = 0; i < H; i++) {
             RankState& R = st[i];
-            LSP_LAUNCH(ctx, k_make_cols_s, unsigned((width_cols + 63) / 64), 64, 0, (const Fr*)lde_of(R), Lr, width_cols, cols_of(R));
+            LSP_LAUNCH(ctx, k_make_cols, unsigned((width_cols + 63) / 64), 64, 0, (const Fr*)lde_of(R), Lr, width_cols, cols_of(R));
             LSP_TRY(merkle_build(ctx, cols_of(R), width_cols, Lr, dig_of(R)));
             send[i] = dig_of(R) + (2 * Lr - 2);
             recv[i] = top_of(R);
@@ -601,7 +546,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_TRY(eval_columns_at(ctx, coef_t, n, W, R.sc + S_ZETA, p_local));
         LSP_TRY(eval_columns_at(ctx, coef_t, n, W, R.sc + S_ZETA_NEXT, p_next));
         for (int c = 0; c < q; c++) LSP_TRY(eval_columns_at(ctx, R.coef_q + size_t(c) * n, n, 1, R.sc + S_CHUNK_PT + c, p_chunks + c));
-        LSP_LAUNCH(ctx, k_open_scalars_s, 1, 1, 0, R.sc + S_ALPHA_FRI, p_local, p_next, p_chunks, int(W), q, R.sc + S_OPEN);
+        LSP_LAUNCH(ctx, k_open_scalars, 1, 1, 0, R.sc + S_ALPHA_FRI, p_local, p_next, p_chunks, int(W), q, R.sc + S_OPEN);
         LSP_TRY(P.get(&R.inv_den[0], Lr * 32));
         LSP_TRY(P.get(&R.inv_den[1], Lr * 32));
         LSP_TRY(inverse_denominators_range(ctx, R.sc + S_ZETA, 2, log_l, size_t(R.rank) * Lr, Lr, R.inv_den));
@@ -702,7 +647,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
                 ln >>= 1;
             }
             Fr* p_final = R.proof + 2 + 2 * W + q + n_rounds;
-            LSP_LAUNCH(ctx, k_final_poly_s, 1, unsigned(ln < 32 ? 32 : ln), 0, (const Fr*)c, log_f, pow2_inverse(log_f), p_final);
+            LSP_LAUNCH(ctx, k_final_poly, 1, unsigned(ln < 32 ? 32 : ln), 0, (const Fr*)c, log_f, host_pow2_inverse(log_f), p_final);
             LSP_TRY(challenger_observe_dev(ctx, R.ch, p_final, int(ln)));
         }
     }
