@@ -32,3 +32,45 @@ def flat_from_dict(proof: dict, indices) -> np.ndarray:
             for v in st["opening_proof"]:
                 put(v)
     return np.array(out, dtype=np.uint64).reshape(-1)
+
+
+def dict_from_flat(words, log_n: int, width: int, log_q: int, fri):
+    """Inverse of flat_from_dict: (proof dict with canonical integers, stored query indices)."""
+    from oracle.field import from_mont_limbs
+    raw = np.asarray(words, dtype=np.uint64).reshape(-1, 4)
+    q = 1 << log_q
+    log_l = log_n + fri.log_blowup
+    rounds = log_n - fri.log_final_poly_len
+    f = 1 << (fri.log_blowup + fri.log_final_poly_len)
+    pos = 0
+
+    def take(k):
+        nonlocal pos
+        out = [from_mont_limbs(r) for r in raw[pos:pos + k]]
+        pos += k
+        return out
+
+    trace_commit, quot_commit = take(2)
+    local, nxt = take(width), take(width)
+    chunks = [[x] for x in take(q)]
+    commits, final_poly = take(rounds), take(f)
+    pow_witness = take(1)[0]
+    queries, indices = [], []
+    for _ in range(fri.num_queries):
+        indices.append(int(raw[pos][0]) if not raw[pos][1:].any() else -1)
+        pos += 1
+        row = take(width)
+        ip = [dict(opened_values=[row], opening_proof=take(log_l))]
+        row = take(q)
+        ip.append(dict(opened_values=[[x] for x in row], opening_proof=take(log_l)))
+        steps = []
+        for r in range(rounds):
+            sib = take(1)[0]
+            steps.append(dict(sibling_value=sib, opening_proof=take(log_l - 1 - r)))
+        queries.append(dict(input_proof=ip, commit_phase_openings=steps))
+    assert pos == len(raw)
+    return dict(commitments=dict(trace=trace_commit, quotient_chunks=quot_commit),
+                opened_values=dict(trace_local=local, trace_next=nxt, quotient_chunks=chunks),
+                opening_proof=dict(commit_phase_commits=commits, query_proofs=queries, final_poly=final_poly,
+                                   pow_witness=pow_witness),
+                degree_bits=log_n), indices

@@ -10,6 +10,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+from oracle import air as OA
 from oracle import cport
 from oracle import dft as OD
 from oracle import field as F
@@ -99,3 +100,30 @@ def test_proof_vectors_python_and_c(case):
         assert proof["commitments"]["quotient_chunks"] == ix(case["quotient_commit"])
         assert list(dbg["query_indices"]) == case["query_indices"]
         check_flat(case, flat_from_dict(proof, dbg["query_indices"]))
+
+
+# ---- frozen rejection reasons of the verifier (tests/golden/golden_verify_v1.json) ------------------------------
+VGOLD = json.loads((Path(__file__).parent / "golden" / "golden_verify_v1.json").read_text())
+
+
+def verify_fixture():
+    """(case, cfgs, publics, words, vectors) of the verify fixture; vectors are (word, bit, expected code)."""
+    case = GOLD["proofs"][VGOLD["proof"]]
+    cfgs, _, publics = instance(case)
+    words = np.array([ix(v) for v in case["flat_words_hex"]], dtype=np.uint64)
+    return case, cfgs, publics, words, [tuple(v) for v in VGOLD["vectors"]]
+
+
+def test_c_port_reproduces_the_frozen_rejection_reasons(p2params):
+    from oracle import cport
+    cport.set_poseidon2(p2params)
+    case, cfgs, publics, words, vectors = verify_fixture()
+    fri = OS.FriConfig(**case["fri"])
+    pub = np.array([F.to_mont_limbs(x) for x in publics], dtype=np.uint64)
+    w = OA.air_width(cfgs)
+    assert cport.verify_limbs(fri, case["log_n"], w, cfgs, pub, words) == 0
+    assert len(vectors) >= 40 and {c for _, _, c in vectors} >= {1, 2, 3, 4}
+    for word, bit, code in vectors:
+        bad = words.copy()
+        bad[word] ^= np.uint64(1 << bit)
+        assert cport.verify_limbs(fri, case["log_n"], w, cfgs, pub, bad) == code, (word, bit)

@@ -50,3 +50,18 @@ def test_proof_vectors(pkg, gctx, case):
     check_flat(case, proof.words)
     gd, idx = proof.to_dict()
     assert gd["commitments"]["trace"] == ix(case["trace_commit"]) and list(idx) == case["query_indices"]
+
+
+def test_device_verifier_reproduces_the_frozen_rejection_reasons(pkg, gctx):
+    """tests/golden/golden_verify_v1.json: one stored proof, 43 single-bit damages, the code each must be rejected with."""
+    import numpy as np
+    from tests.test_golden import verify_fixture
+    case, cfgs, publics, words, vectors = verify_fixture()
+    g = [pkg.AirPermutationConfig(x.a_columns_ids, x.b_columns_ids, x.b_inverse_id, x.check_id) for x in cfgs]
+    fri = pkg.FriConfig(**case["fri"])
+    w = sum(c.width() for c in g)
+    assert pkg.verify_code(gctx, fri, g, words, publics, case["log_n"], w) == 0
+    for word, bit, code in vectors:
+        bad = words.copy()
+        bad[word] ^= np.uint64(1 << bit)
+        assert pkg.verify_code(gctx, fri, g, bad, publics, case["log_n"], w) == code, (word, bit)
