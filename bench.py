@@ -189,7 +189,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "prove_seconds", "value": v, "unit": "s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "u256 (BLS12-377 Fr, Montgomery 4x64-bit)", "data": "synthetic",
-        "config": workload_config(args, 1),
+        "config": workload_config(args, world),   # the arm being compared against: same workload object
         "cpu_baseline": {"value": v, "unit": "s", "cores": info["threads"], "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     })
