@@ -12,6 +12,22 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
 
 
+def pytest_sessionstart(session):
+    """A fresh checkout has no built artefacts (they are git-ignored): build them once, exactly as
+    `__graft_entry__.build()` does, instead of failing every test that loads the library or the C oracle.
+    Nothing is rebuilt when both shared objects are already there (the GPU box receives them prebuilt)."""
+    lib = ROOT / "linea-stark-prover_b200" / "liblsp_b200.so"
+    orc = ROOT / "oracle" / "c" / "liblsp_oracle.so"
+    exe = ROOT / "linea-stark-prover_b200" / "lsp_prove"
+    if lib.exists() and orc.exists() and exe.exists():
+        return
+    import shutil
+    if shutil.which("nvcc") is None and not Path("/usr/local/cuda/bin/nvcc").exists():
+        return      # nothing to build with: the tests that need the library will say so
+    import __graft_entry__ as g
+    g.build()
+
+
 @pytest.fixture(scope="session")
 def pkg():
     import __graft_entry__ as g
