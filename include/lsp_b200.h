@@ -177,6 +177,10 @@ int lsp_cbor_permutation_decode(const uint8_t* cbor, size_t len, uint8_t* be_row
 int lsp_cbor_permutation_read(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_cols, char* name, size_t name_cap,
                               uint8_t** be_rowmajor_out);
 void lsp_host_free(void* p);
+/* Process-wide switch: after lsp_host_pinned(1) the `_read` functions hand out PAGE-LOCKED buffers (portable across the
+ * process's devices), recycled through a small pool on lsp_host_free, so that `lsp_*_trace_be` uploads at PCIe rate and
+ * several ranks may read one buffer at once.  lsp_host_pinned(0) returns to malloc and releases the pooled blocks. */
+int lsp_host_pinned(int enable);
 /* `RawLookupTrace::read_file` (trace/src/lookup.rs:20-44), same conventions.  Row layout of the decoded
  * buffer: a columns, b columns table by table, a_filter, one b_filter per table -- i.e. the first
  * n_a + T*n_b + 1 + T columns of the trace `get_trace` emits (:63-71).  Filter entries the file omits

@@ -97,6 +97,7 @@ SIGNATURES = {
     "lsp_cbor_lookup_read": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                        C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "lsp_host_free": (None, [C.c_void_p]),
+    "lsp_host_pinned": (C.c_int, [C.c_int]),
     "lsp_lookup_trace": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.POINTER(vp)]),
     "lsp_lookup_trace_be": (C.c_int, [vp, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.POINTER(vp)]),
     "lsp_mat_hconcat": (C.c_int, [vp, C.POINTER(vp), C.c_int, C.POINTER(vp)]),

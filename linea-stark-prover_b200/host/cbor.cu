@@ -20,9 +20,13 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <cuda_runtime.h>
 
 #include "../../include/lsp_b200.h"
 
@@ -596,7 +600,70 @@ void copy_name(const std::string& from, char* name, size_t name_cap) {
     name[n] = 0;
 }
 
+// ---- output buffers of the `_read` entry points ------------------------------------------------------------
+// Plain malloc by default.  After lsp_host_pinned(1) they are page-locked (cudaHostAllocPortable: DMA-able from every
+// device of the process), so the upload that follows runs at PCIe rate instead of through the driver's staging path,
+// and eight ranks can read the same buffer at once.  Pinning costs ~0.4 ms per MB, so freed blocks are kept and
+// handed out again (best fit): a prover that reads file after file pins once.
+struct PinnedPool {
+    std::mutex mu;
+    bool enabled = false;
+    std::map<void*, size_t> live;                 // handed out
+    std::multimap<size_t, void*> spare;           // returned, by size
+} g_pool;
+
+void* host_alloc(size_t n) {
+    if (n == 0) n = 1;
+    {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        if (!g_pool.enabled) return malloc(n);
+        auto it = g_pool.spare.lower_bound(n);
+        if (it != g_pool.spare.end()) {
+            void* p = it->second;
+            g_pool.live[p] = it->first;
+            g_pool.spare.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, n, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();                       // no device / no lockable memory: an ordinary buffer still works
+        return malloc(n);
+    }
+    std::lock_guard<std::mutex> lock(g_pool.mu);
+    g_pool.live[p] = n;
+    return p;
+}
+
+void host_release(void* p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        auto it = g_pool.live.find(p);
+        if (it != g_pool.live.end()) {
+            g_pool.spare.emplace(it->second, p);
+            g_pool.live.erase(it);
+            return;
+        }
+    }
+    free(p);
+}
+
 }  // namespace
+
+extern "C" int lsp_host_pinned(int enable) {
+    std::vector<void*> drop;
+    {
+        std::lock_guard<std::mutex> lock(g_pool.mu);
+        g_pool.enabled = enable != 0;
+        if (!g_pool.enabled) {
+            for (auto& kv : g_pool.spare) drop.push_back(kv.second);
+            g_pool.spare.clear();
+        }
+    }
+    for (void* p : drop) cudaFreeHost(p);
+    return LSP_OK;
+}
 
 extern "C" int lsp_cbor_lookup_shape(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_a_cols, uint32_t* n_tables,
                                      uint32_t* n_b_cols, char* name, size_t name_cap) {
@@ -629,10 +696,10 @@ extern "C" int lsp_cbor_lookup_read(const uint8_t* cbor, size_t len, size_t* row
     std::vector<Run> runs;
     if (!lookup_shape(cbor, len, s, &runs) || s.height() == 0) return LSP_ERR_PARAM;
     const size_t h = s.height(), stride = s.a_rows.size() + s.b_rows.size() * (s.b_rows[0].size() + 1) + 1;
-    uint8_t* out = static_cast<uint8_t*>(malloc(h * stride * 32));
+    uint8_t* out = static_cast<uint8_t*>(host_alloc(h * stride * 32));
     if (!out) return LSP_ERR_NOMEM;
     if (!fill_lookup(cbor, len, s, runs, out, h)) {
-        free(out);
+        host_release(out);
         return LSP_ERR_PARAM;
     }
     *rows = h;
@@ -671,10 +738,10 @@ extern "C" int lsp_cbor_permutation_read(const uint8_t* cbor, size_t len, size_t
     std::vector<Run> runs;
     if (!permutation_shape(cbor, len, s, &runs) || s.height() == 0) return LSP_ERR_PARAM;
     const size_t h = s.height(), nc = s.a_rows.size();
-    uint8_t* out = static_cast<uint8_t*>(malloc(h * 2 * nc * 32));
+    uint8_t* out = static_cast<uint8_t*>(host_alloc(h * 2 * nc * 32));
     if (!out) return LSP_ERR_NOMEM;
     if (!fill_permutation(cbor, len, s, runs, out, h)) {
-        free(out);
+        host_release(out);
         return LSP_ERR_PARAM;
     }
     *rows = h;
@@ -684,4 +751,4 @@ extern "C" int lsp_cbor_permutation_read(const uint8_t* cbor, size_t len, size_t
     return LSP_OK;
 }
 
-extern "C" void lsp_host_free(void* p) { free(p); }
+extern "C" void lsp_host_free(void* p) { host_release(p); }

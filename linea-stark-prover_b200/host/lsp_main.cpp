@@ -218,6 +218,7 @@ int main(int argc, char** argv) {
         if (gpus > 1) CHECK(r.ctx, lsp_comm_init_nccl(r.ctx, k, gpus, nccl_id, &r.comm));
     });
     lsp_ctx* ctx = ranks[0].ctx;
+    lsp_host_pinned(1);   // parsed columns land in page-locked memory: every rank uploads them at PCIe rate; pinned once, reused by --repeat
 
     // One pass of main's body.  --repeat N runs it N times in one process: the first pass pays for the CUDA context,
     // the memory pool and the twiddle / selector tables; later passes are what a long-running prover sees.
@@ -389,6 +390,7 @@ int main(int argc, char** argv) {
         if (repeat > 1) printf("---- pass %d of %d ----\n", rep + 1, repeat);
         status = run_once();
     }
+    lsp_host_pinned(0);
     on_all_ranks(ranks, [&](Rank& r, int) {
         if (r.comm) lsp_comm_destroy(r.comm);
         lsp_ctx_destroy(r.ctx);

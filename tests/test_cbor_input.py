@@ -256,3 +256,23 @@ def test_single_pass_read_equals_shape_plus_decode(pkg, monkeypatch):
             pkg.read_permutation_trace_once(bad)
     with pytest.raises(pkg.BackendError):
         pkg.read_lookup_trace_once(lblob[:300])
+
+
+def test_pinned_output_buffers_fall_back_to_ordinary_memory_without_a_device(pkg):
+    """`lsp_host_pinned(1)` asks for page-locked `_read` buffers; where nothing can be pinned (this CPU-only container) the
+    reader must still work on an ordinary buffer, and blocks handed back must be reusable."""
+    lib = pkg.ffi.load()
+    a, b = OT.synthetic_permutation_input(9, 2, 40)
+    blob = OT.encode_raw_permutation_trace(a, b, "pin")
+    want = pkg.read_raw_permutation_trace(blob)
+    assert lib.lsp_host_pinned(1) == 0
+    try:
+        for _ in range(3):                                   # alloc, release into the pool, alloc again
+            buf, rows, nc, name = pkg.read_permutation_trace_once(blob)
+            assert (rows, nc, name) == want[1:] and np.array_equal(buf.array, want[0])
+            buf.free()
+    finally:
+        assert lib.lsp_host_pinned(0) == 0
+    buf, *_ = pkg.read_permutation_trace_once(blob)
+    assert np.array_equal(buf.array, want[0])
+    buf.free()
