@@ -6,14 +6,14 @@
 //   1. k_verify_transcript (stark.cu)  one warp replays the whole Fiat-Shamir transcript: alpha, zeta,
 //                                      the FRI batching challenge, every beta, the proof-of-work check
 //                                      and all query indices.  Nothing in it depends on query data.
-//   2. k_verify_fold                   one thread per query: index check, reduced opening at the queried
+//   2. k_verify_fold_ood               one thread per query: index check, reduced opening at the queried
 //                                      point (two inversions), the fold chain through every round (the
 //                                      round points are a squaring chain, no inversion), final-polynomial
 //                                      check.  Writes the leaf pair of every commit-phase opening.
-//   3. k_verify_path_jobs + k_merkle_paths   one thread per (query, tree) Merkle path -- trace, quotient,
+//   3. k_verify_path_jobs + k_merkle_paths_tri   three lanes per (query, tree) Merkle path -- trace, quotient,
 //                                      one per FRI round: 33 x 21 independent paths at the baseline shape.
-//   4. k_verify_ood                    quotient recombination and the AIR constraints at zeta, through
-//                                      the same fold_air_constraints the quotient kernel uses.
+//      (last block of launch 2)        quotient recombination and the AIR constraints at zeta, through the same
+//                                      fold_air_constraints the quotient kernel uses; every inversion on its own thread.
 // The host then reads one small status block and reports the FIRST failing check in the
 // reference verifier's order, so a rejected proof yields the same reason as the CPU verifier.
 //
@@ -34,38 +34,42 @@ struct PathJob {
     int width, log_h;
 };
 
-// MerkleTreeMmcs::verify_batch for one matrix: hash the row (PaddingFreeSponge, rate 2), then
-// compress with the siblings up to the root.  Sponge steps and tree levels share ONE inlined
-// permutation site.
+// MerkleTreeMmcs::verify_batch for one matrix: hash the row (PaddingFreeSponge, rate 2), then compress with the
+// siblings up to the root -- on three lanes per path (p2_permute_tri: 30 S-box latencies per permutation instead of
+// 46).  Sponge steps and tree levels share ONE inlined permutation site.  A warp carries ten paths; every lane runs as
+// many permutations as the longest of them, shorter paths keep their result aside.
 template <int D>
-__global__ void __launch_bounds__(32) k_merkle_paths(const __grid_constant__ P2Params P, const PathJob* __restrict__ jobs, int n_jobs) {
-    LSP_P2_SLOT_DECL(32);
-    const int t = blockIdx.x * 32 + threadIdx.x;
-    const bool live = t < n_jobs;
+__global__ void __launch_bounds__(32) k_merkle_paths_tri(const __grid_constant__ P2Params P, const PathJob* __restrict__ jobs, int n_jobs) {
+    const int lane = threadIdx.x, k = lane / 3, w = lane - 3 * k;
+    const int t = blockIdx.x * 10 + k;
+    const bool live = k < 10 && t < n_jobs;
     const PathJob J = jobs[live ? t : 0];
-    const int n_leaf = (J.width + 1) / 2, total = n_leaf + J.log_h;
-    Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
+    const int n_leaf = (J.width + 1) / 2, total = live ? n_leaf + J.log_h : 0;
+    const int longest = __reduce_max_sync(0xffffffffu, total);
+    Fr s = fr_zero(), result = fr_zero();
 #pragma unroll 1
-    for (int step = 0; step < total; step++) {
+    for (int step = 0; step < longest; step++) {
+        // word 0 of the triple's state, for the compress steps (all lanes take part in the shuffle)
+        Fr node;
+#pragma unroll
+        for (int i = 0; i < 8; i++) node.l[i] = __shfl_sync(0xffffffffu, s.l[i], 3 * k < 30 ? 3 * k : 30);
         if (step < n_leaf) {
-            const int c = 2 * step;
-            s0 = fr_load(J.row + c);
-            if (c + 1 < J.width) s1 = fr_load(J.row + c + 1);  // odd tail: state[1] keeps its stale value
-        } else {
-            const int k = step - n_leaf;
-            const Fr sib = fr_load(J.sibs + k), node = s0;
-            const bool right = (J.index >> k) & 1u;
-            s0 = right ? sib : node;
-            s1 = right ? node : sib;
-            s2 = fr_zero();
+            const int c = 2 * step + w;                         // w = 2: the capacity word carries over
+            if (w < 2 && c < J.width) s = fr_load(J.row + c);   // odd tail: word 1 keeps its stale value
+        } else if (step < total) {
+            const int lvl = step - n_leaf;
+            const Fr sib = fr_load(J.sibs + lvl);
+            const bool right = (J.index >> lvl) & 1u;
+            s = w == 2 ? fr_zero() : ((w == 0) == right ? sib : node);
         }
-        p2_permute<D, 32>(P, s0, s1, s2, LSP_P2_SLOT(32));
+        p2_permute_tri<D>(P, s, w, 3 * k < 30 ? 3 * k : 30);
+        if (step == total - 1) result = s;
     }
-    if (live) {
+    if (live && w == 0) {
         const Fr root = fr_load(J.root);
         bool same = true;
 #pragma unroll
-        for (int i = 0; i < 8; i++) same = same && (root.l[i] == s0.l[i]);
+        for (int i = 0; i < 8; i++) same = same && (root.l[i] == result.l[i]);
         *J.bad = same ? 0 : 1;
     }
 }
@@ -102,8 +106,7 @@ __device__ __forceinline__ bool fr_same(const Fr& a, const Fr& b) {
 }
 
 // verify_query for one query: open_input's reduced opening, then the fold chain.
-__global__ void __launch_bounds__(32) k_verify_fold(const __grid_constant__ VerifyArgs A) {
-    const int qi = blockIdx.x * 32 + threadIdx.x;
+__device__ __forceinline__ void verify_fold_one(const VerifyArgs& A, int qi) {
     if (qi >= A.n_queries) return;
     const uint32_t index = A.idx[qi];
     const Fr* in = A.p_queries + size_t(qi) * A.per_query;
@@ -211,23 +214,40 @@ __global__ void k_verify_path_jobs(const __grid_constant__ VerifyArgs A, PathJob
 }
 
 // Out-of-domain check: sum_i zp_i(zeta) * chunk_i(zeta) == folded_constraints(zeta) / Z_H(zeta).
-// Threads (i, j), i != j, compute the factors of zp_i; thread 0 finishes.
-__global__ void __launch_bounds__(64) k_verify_ood(const __grid_constant__ VerifyArgs A) {
+// One block of VERIFY_BLOCK threads.  Every inversion the identity needs runs on its own thread -- the q(q-1) cross factors
+// of the zp_i on threads (i, j), 1/(zeta - 1), 1/(zeta - w_N^-1) and 1/Z_H(zeta) on three more -- so the depth is ONE
+// Fermat inversion; 1/shift_j is a power of the inverse generators, not an inversion.  Thread 0 finishes.
+constexpr int VERIFY_BLOCK = 96;
+__device__ __forceinline__ void verify_ood_block(const VerifyArgs& A) {
     __shared__ Fr factor[64];
+    __shared__ Fr inv3[3];   // 1/(zeta - 1), 1/(zeta - w_N^-1), 1/Z_H(zeta)
     const int t = threadIdx.x, q = A.q, i = t / q, j = t - i * q;
     const Fr zeta = fr_load(A.scal + VT_ZETA);
     const Fr one = fr_one();
     if (t < q * q && i != j) {
-        const Fr wnq = fr_two_adic_generator(A.log_n + A.log_q);
-        const Fr g = fr_const(FR_GEN);
-        const Fr shift_i = fr_mul(g, fr_pow_u32(wnq, uint32_t(i))), shift_j = fr_mul(g, fr_pow_u32(wnq, uint32_t(j)));
-        const Fr sj_inv = fr_inv(shift_j);
-        Fr a = fr_mul(zeta, sj_inv), b = fr_mul(shift_i, sj_inv);
+        const int lnq = A.log_n + A.log_q;
+        const Fr wnq = fr_two_adic_generator(lnq);
+        const uint32_t mask = uint32_t((size_t(1) << lnq) - 1);
+        // shift_k = g * w_{Nq}^k:  zeta / shift_j = zeta * g^-1 * w^-j,   shift_i / shift_j = w^(i-j)
+        Fr a = fr_mul(fr_mul(zeta, fr_const(FR_GEN_INV)), fr_pow_u32(wnq, (0u - uint32_t(j)) & mask));
+        Fr b = fr_pow_u32(wnq, (uint32_t(i) - uint32_t(j)) & mask);
         for (int k = 0; k < A.log_n; k++) {
             a = fr_sqr(a);
             b = fr_sqr(b);
         }
         factor[t] = fr_mul(fr_sub(a, one), fr_inv(fr_sub(b, one)));
+    }
+    if (t >= 64 && t < 67) {
+        const Fr wn_inv = fr_pow_u32(fr_two_adic_generator(A.log_n), uint32_t((size_t(1) << A.log_n) - 1));
+        Fr v;
+        if (t == 64) v = fr_sub(zeta, one);
+        else if (t == 65) v = fr_sub(zeta, wn_inv);
+        else {
+            Fr zn = zeta;
+            for (int k = 0; k < A.log_n; k++) zn = fr_sqr(zn);
+            v = fr_sub(zn, one);
+        }
+        inv3[t - 64] = fr_inv(v);
     }
     __syncthreads();
     if (t != 0) return;
@@ -242,12 +262,21 @@ __global__ void __launch_bounds__(64) k_verify_ood(const __grid_constant__ Verif
     for (int k = 0; k < A.log_n; k++) zn = fr_sqr(zn);
     const Fr z_h = fr_sub(zn, one);
     const Fr wn_inv = fr_pow_u32(fr_two_adic_generator(A.log_n), uint32_t((size_t(1) << A.log_n) - 1));
-    const Fr is_first = fr_mul(z_h, fr_inv(fr_sub(zeta, one)));
-    const Fr is_last = fr_mul(z_h, fr_inv(fr_sub(zeta, wn_inv)));
+    const Fr is_first = fr_mul(z_h, inv3[0]);
+    const Fr is_last = fr_mul(z_h, inv3[1]);
     const Fr is_trans = fr_sub(zeta, wn_inv);
     const Fr folded = fold_air_constraints(A.cfg, A.p_local, 1, 0, size_t(A.W), fr_load(A.publics), fr_load(A.publics + 1),
                                            fr_load(A.scal + VT_ALPHA), is_first, is_last, is_trans);
-    *A.ood_bad = fr_same(fr_mul(folded, fr_inv(z_h)), quotient) ? 0 : 1;
+    *A.ood_bad = fr_same(fr_mul(folded, inv3[2]), quotient) ? 0 : 1;
+}
+
+// Fold chains and the out-of-domain identity depend on the transcript only, not on each other: one launch, the last
+// block takes the identity, the others one query per thread.
+__global__ void __launch_bounds__(VERIFY_BLOCK) k_verify_fold_ood(const __grid_constant__ VerifyArgs A) {
+    if (blockIdx.x + 1 == gridDim.x)
+        verify_ood_block(A);
+    else
+        verify_fold_one(A, int(blockIdx.x) * VERIFY_BLOCK + int(threadIdx.x));
 }
 
 }  // namespace lsp
@@ -357,10 +386,9 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     LSP_CUDA(ctx, cudaMemsetAsync(status + 2, 0, 4, ctx->stream));
     LSP_LAUNCH(ctx, k_verify_canonical, grid_for(ctx, proof_elems, 128), 128, 0, (const Fr*)proof, proof_elems, status + 2);
     LSP_TRY(verify_transcript(ctx, ch, T));
-    LSP_LAUNCH(ctx, k_verify_fold, unsigned((nq + 31) / 32), 32, 0, A);
+    LSP_LAUNCH(ctx, k_verify_fold_ood, unsigned((nq + VERIFY_BLOCK - 1) / VERIFY_BLOCK + 1), VERIFY_BLOCK, 0, A);
     LSP_LAUNCH(ctx, k_verify_path_jobs, unsigned((n_jobs + 127) / 128), 128, 0, A, jobs);
-    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_merkle_paths<D>, unsigned((n_jobs + 31) / 32), 32, 0, ctx->p2, (const PathJob*)jobs, n_jobs));
-    LSP_LAUNCH(ctx, k_verify_ood, 1, 64, 0, A);
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_merkle_paths_tri<D>, unsigned((n_jobs + 9) / 10), 32, 0, ctx->p2, (const PathJob*)jobs, n_jobs));
     LSP_CUDA(ctx, cudaMemcpyAsync(status + n_status, &ch->overflow, 4, cudaMemcpyDeviceToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, status, (n_status + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
     cudaEventRecord(ev1, ctx->stream);
@@ -421,7 +449,7 @@ extern "C" int lsp_merkle_verify_batch(lsp_ctx* ctx, const uint64_t root[4], uin
     J.log_h = int(log_height);
     LSP_CUDA(ctx, cudaMemcpyAsync(job, &J, sizeof(J), cudaMemcpyHostToDevice, ctx->stream));
     LSP_CUDA(ctx, cudaMemsetAsync(bad, 0xff, 4, ctx->stream));
-    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_merkle_paths<D>, 1, 32, 0, ctx->p2, (const PathJob*)job, 1));
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_merkle_paths_tri<D>, 1, 32, 0, ctx->p2, (const PathJob*)job, 1));
     LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, bad, 4, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return *static_cast<const int*>(ctx->pinned) ? LSP_VERIFY_ROOT_MISMATCH : LSP_OK;
