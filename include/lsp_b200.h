@@ -58,8 +58,13 @@ uint64_t lsp_kernel_launches(const lsp_ctx* ctx);
  * [{"phase","kernel","launches","ms"},...]. */
 int lsp_kernel_timing(lsp_ctx* ctx, int enable);
 int lsp_kernel_timing_report(lsp_ctx* ctx, char* buf, size_t cap);
-/* Measured issue rate of independent IMAD.WIDE.U32 (32x32+64 MACs per second) on this
- * device: the denominator of the integer roofline the benchmark reports. */
+/* Measured rate (32x32->64 multiply-accumulates per second) of each instruction form the multiply can take on
+ * this device, with data-dependent operands: [0] IMAD.WIDE.U32 multiply-only + IADD3/IADD3.X accumulate,
+ * [1] IMAD.WIDE.U32 with fused 64-bit accumulate, [2] IMAD.WIDE.U32.X (carry in and out), [3] the IMAD + IMAD.HI
+ * pair (SASS: profiles/sass_k_int_peak.txt).  lsp_int_peak returns the fastest of them: the denominator of the
+ * integer roofline the benchmark reports. */
+#define LSP_INT_PEAK_FORMS 4
+int lsp_int_peaks(lsp_ctx* ctx, double mac32_per_s[LSP_INT_PEAK_FORMS]);
 int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s);
 
 /* `Perm::new_from_rng(8, 22, &mut rng)` (bin/src/main.rs:49): the host draws the
@@ -149,7 +154,10 @@ int lsp_quotient_permutation(lsp_ctx* ctx, const lsp_mat* lde_bitrev, int log_n,
 int lsp_quotient_air(lsp_ctx* ctx, const lsp_mat* lde_bitrev, int log_n, int log_q,
                      const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms,
                      const uint64_t publics[2][4], const uint64_t alpha[4], lsp_mat** chunks_out);
-/* log2 of the number of quotient chunks `prove` uses for this AIR (`get_log_quotient_degree`). */
+/* log2 of the number of quotient chunks `prove` uses for this AIR: `get_log_quotient_degree` of p3-uni-stark, i.e.
+ * `LineaAIR::eval` (air/src/lib.rs:47-54) evaluated on symbolic degrees, log2_ceil(max(d_max, 2) - 1).  The `_cfg`
+ * form walks the actual configs (what prove and verify use); the count form assumes non-empty configs. */
+int lsp_air_log_quotient_degree_cfg(const lsp_lookup_air_cfg* lookups, int n_lookups, const lsp_perm_air_cfg* perms, int n_perms);
 int lsp_air_log_quotient_degree(int n_lookups, int n_perms);
 
 /* ---- FRI pieces of `TwoAdicFriPcs` (bin/src/config.rs:24-25) -------------- */

@@ -90,6 +90,15 @@ class Context:
         self.check(self.lib.lsp_int_peak(self.h, C.byref(v)), "lsp_int_peak")
         return v.value
 
+    INT_PEAK_FORMS = ("IMAD.WIDE.U32 (multiply only) + IADD3 + IADD3.X", "IMAD.WIDE.U32 (fused 64-bit accumulate)",
+                      "IMAD.WIDE.U32.X (carry in and out)", "IMAD + IMAD.HI.U32")
+
+    def int_peaks(self) -> dict:
+        """32x32->64 multiply-accumulates per second of every instruction form (lsp_int_peaks)."""
+        v = (C.c_double * len(self.INT_PEAK_FORMS))()
+        self.check(self.lib.lsp_int_peaks(self.h, v), "lsp_int_peaks")
+        return dict(zip(self.INT_PEAK_FORMS, [float(x) for x in v]))
+
     def permutation_trace(self, ab_limbs: np.ndarray, n: int, c: int, publics_limbs: np.ndarray) -> "Mat":
         """`RawPermutationTrace::get_trace` + `RawTrace::get_trace` on the device.
         ab_limbs: uint64[n*2c,4] row-major (a columns then b columns), Montgomery limbs."""

@@ -270,10 +270,16 @@ extern "C" int lsp_kernel_timing_report(lsp_ctx* ctx, char* buf, size_t cap) {
     return LSP_OK;
 }
 
-// Integer-pipe peak of this device: eight independent IMAD.WIDE.U32 chains per thread with a
-// data-dependent multiplicand (the instruction the Montgomery product is made of; with
-// loop-invariant operands ptxas strength-reduces the multiply away and the "peak" doubles).
-// Timed with CUDA events.  Denominator of the integer roofline: 32x32->64 MACs per second.
+// Integer-pipe peaks of this device: the 32x32->64 multiply-accumulate in each instruction form the
+// compiler can emit for it, eight independent accumulators per thread, DATA-DEPENDENT multiplicands
+// (with loop-invariant operands ptxas hoists the product and the "multiply" becomes an add).  The SASS
+// of each form is committed under profiles/sass_k_int_peak.txt.  Timed with CUDA events on the ctx stream.
+//   form 0  IMAD.WIDE.U32 Rd, Ra, Rb, RZ + IADD3 + IADD3.X   multiply only, the 64-bit accumulation on the ALU pipe
+//           (what ptxas makes of mad.wide.u32 here: it splits the add off to shorten the multiplicand's dependency)
+//   form 1  IMAD.WIDE.U32 Rd, Ra, Rb, Rc                     fused 64-bit multiply-accumulate, no carry in or out
+//   form 2  IMAD.WIDE.U32.X Rd, P, Ra, Rb, Rc, P             carry in and out: the link the Montgomery product is made of
+//   form 3  IMAD + IMAD.HI.U32                               the pair ptxas falls back to when it cannot fuse
+template <int FORM>
 __global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, uint32_t seed, int iters) {
     uint32_t b = blockIdx.x * 40503u + 17u + seed + threadIdx.x * 2654435761u;
     uint32_t lo[8], hi[8];
@@ -283,17 +289,29 @@ __global__ void __launch_bounds__(256) k_int_peak(uint32_t* out, uint32_t seed, 
         hi[c] = (b ^ c) * 0x7f4a7c15u;
     }
     for (int it = 0; it < iters; it++) {
+        if (FORM == 2) asm volatile("add.cc.u32 %0, %0, %1;" : "+r"(b) : "r"(lo[0]));  // opens the carry chain
 #pragma unroll
-        for (int c = 0; c < 8; c++)  // (lo,hi)[c] += lo[c+1] * b : one IMAD.WIDE.U32 with 64-bit accumulate
-            asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[c]), "+r"(hi[c]) : "r"(lo[(c + 1) & 7]), "r"(b));
+        for (int c = 0; c < 8; c++) {  // (lo,hi)[c] += lo[c+1] * b
+            if (FORM == 0) {
+                unsigned long long t = (static_cast<unsigned long long>(hi[c]) << 32) | lo[c];
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(t) : "r"(lo[(c + 1) & 7]), "r"(b));
+                lo[c] = uint32_t(t);
+                hi[c] = uint32_t(t >> 32);
+            } else if (FORM == 1)
+                asm volatile("mad.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.u32 %1, %2, %3, %1;" : "+r"(lo[c]), "+r"(hi[c]) : "r"(lo[(c + 1) & 7]), "r"(b));
+            else if (FORM == 2)
+                asm volatile("madc.lo.cc.u32 %0, %2, %3, %0;\n\tmadc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo[c]), "+r"(hi[c]) : "r"(lo[(c + 1) & 7]), "r"(b));
+            else
+                asm volatile("mad.lo.u32 %0, %2, %3, %0;\n\tmad.hi.u32 %1, %2, %3, %1;" : "+r"(lo[c]), "+r"(hi[c]) : "r"(hi[(c + 1) & 7]), "r"(b));
+        }
     }
-    uint32_t r = 0;
+    uint32_t r = b;
 #pragma unroll
     for (int c = 0; c < 8; c++) r ^= lo[c] ^ hi[c];
     out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
-extern "C" int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s) {
+extern "C" int lsp_int_peaks(lsp_ctx* ctx, double mac32_per_s[LSP_INT_PEAK_FORMS]) {
     if (!ctx || !mac32_per_s) return LSP_ERR_PARAM;
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
     const int blocks = ctx->sm_count * 8, threads = 256, iters = 8192;
@@ -303,21 +321,39 @@ extern "C" int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    float best = 1e30f;
-    for (int r = 0; r < 6; r++) {
-        cudaEventRecord(e0, ctx->stream);
-        k_int_peak<<<blocks, threads, 0, ctx->stream>>>(out, uint32_t(r), iters);
-        cudaEventRecord(e1, ctx->stream);
-        cudaEventSynchronize(e1);
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e0, e1);
-        if (r >= 2 && ms < best) best = ms;
+    for (int form = 0; form < LSP_INT_PEAK_FORMS; form++) {
+        float best = 1e30f;
+        for (int r = 0; r < 6; r++) {
+            cudaEventRecord(e0, ctx->stream);
+            switch (form) {
+                case 0: k_int_peak<0><<<blocks, threads, 0, ctx->stream>>>(out, uint32_t(r), iters); break;
+                case 1: k_int_peak<1><<<blocks, threads, 0, ctx->stream>>>(out, uint32_t(r), iters); break;
+                case 2: k_int_peak<2><<<blocks, threads, 0, ctx->stream>>>(out, uint32_t(r), iters); break;
+                default: k_int_peak<3><<<blocks, threads, 0, ctx->stream>>>(out, uint32_t(r), iters); break;
+            }
+            cudaEventRecord(e1, ctx->stream);
+            cudaEventSynchronize(e1);
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e0, e1);
+            if (r >= 2 && ms < best) best = ms;
+        }
+        ctx->launches += 6;
+        mac32_per_s[form] = double(blocks) * threads * iters * 8.0 / (best * 1e-3);
     }
-    ctx->launches += 6;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     LSP_CUDA(ctx, cudaGetLastError());
-    *mac32_per_s = double(blocks) * threads * iters * 8.0 / (best * 1e-3);
+    return LSP_OK;
+}
+
+// The fastest of the forms above: the denominator of the integer roofline.
+extern "C" int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s) {
+    if (!mac32_per_s) return LSP_ERR_PARAM;
+    double v[LSP_INT_PEAK_FORMS];
+    LSP_TRY(lsp_int_peaks(ctx, v));
+    *mac32_per_s = v[0];
+    for (int i = 1; i < LSP_INT_PEAK_FORMS; i++)
+        if (v[i] > *mac32_per_s) *mac32_per_s = v[i];
     return LSP_OK;
 }
 

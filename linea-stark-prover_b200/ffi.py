@@ -53,6 +53,7 @@ SIGNATURES = {
     "lsp_kernel_timing": (C.c_int, [vp, C.c_int]),
     "lsp_kernel_timing_report": (C.c_int, [vp, C.c_char_p, C.c_size_t]),
     "lsp_int_peak": (C.c_int, [vp, C.POINTER(C.c_double)]),
+    "lsp_int_peaks": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "lsp_permutation_trace": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, u64p, C.POINTER(vp)]),
     "lsp_set_poseidon2": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, u64p, u64p]),
     "lsp_fr_op": (C.c_int, [vp, C.c_int, u64p, u64p, u64p, C.c_size_t]),
@@ -87,6 +88,7 @@ SIGNATURES = {
     "lsp_prove_air_sharded_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(LookupAirCfg), C.c_int, C.POINTER(PermAirCfg),
                                             C.c_int, u64p, u64p, C.c_size_t, f32p]),
     "lsp_air_log_quotient_degree": (C.c_int, [C.c_int, C.c_int]),
+    "lsp_air_log_quotient_degree_cfg": (C.c_int, [C.POINTER(LookupAirCfg), C.c_int, C.POINTER(PermAirCfg), C.c_int]),
     "lsp_cbor_permutation_shape": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t]),
     "lsp_cbor_permutation_decode": (C.c_int, [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_uint32]),
     "lsp_cbor_lookup_shape": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),

@@ -1,5 +1,7 @@
-// Multi-GPU prove: one proof sharded over G GPUs by ROW RANGES of the bit-reversed LDE
-// (SURVEY.md 8(e)).  Rank r owns storage rows [r*L/G, (r+1)*L/G) of every committed matrix,
+// `p3_uni_stark::prove` over `TwoAdicFriPcs` (bin/src/main.rs:80-86), THE implementation: one proof on G >= 1
+// GPUs, sharded by ROW RANGES of the bit-reversed LDE.  The single-GPU entry points
+// (lsp_prove_air[_dev], host/prover.cu) call this code with a one-rank communicator, so there is one prover to keep
+// bit-exact, not two.  Rank r owns storage rows [r*L/G, (r+1)*L/G) of every committed matrix,
 // i.e. 2^log_blowup / G whole cosets of the evaluation domain, so
 //   * the coset LDE of its rows needs no traffic (coefficients are replicated: every rank
 //     interpolates the full trace once);
@@ -24,6 +26,7 @@
 #include <nccl.h>
 
 #include "../csrc/stark.cuh"
+#include "comm.hpp"
 #include "prove_kernels.cuh"
 
 using namespace lsp;
@@ -72,18 +75,6 @@ NcclApi* nccl_api() {
 
 }  // namespace
 
-struct lsp_comm {
-    lsp_ctx* ctx = nullptr;
-    int world = 1;
-    int rank = 0;        // rank of this process (NCCL mode); unused in local mode
-    bool local = false;  // all ranks hosted in this process on ctx's device
-    ncclComm_t nccl = nullptr;
-    // reusable upload buffers of lsp_prove_air_sharded (row-major staging, column-major trace)
-    Fr* up_stage = nullptr;
-    Fr* up_mat = nullptr;
-    size_t up_elems = 0;
-};
-
 namespace {
 
 #define LSP_NCCL(ctx, call)                                                                                   \
@@ -105,7 +96,7 @@ int coll_allgather(lsp_comm* cm, const std::vector<int>& ranks, const std::vecto
                 LSP_CUDA(ctx, cudaMemcpyAsync((char*)recv[d] + size_t(ranks[s]) * bytes, send[s], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         return LSP_OK;
     }
-    LSP_NCCL(ctx, nccl_api()->AllGather(send[0], recv[0], bytes / 8, ncclUint64, cm->nccl, ctx->stream));
+    LSP_NCCL(ctx, nccl_api()->AllGather(send[0], recv[0], bytes / 8, ncclUint64, ((ncclComm_t)cm->nccl), ctx->stream));
     return LSP_OK;
 }
 int coll_broadcast(lsp_comm* cm, const std::vector<int>& ranks, int root, const std::vector<void*>& buf, size_t bytes) {
@@ -116,7 +107,7 @@ int coll_broadcast(lsp_comm* cm, const std::vector<int>& ranks, int root, const 
                 LSP_CUDA(ctx, cudaMemcpyAsync(buf[d], buf[root], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
         return LSP_OK;
     }
-    LSP_NCCL(ctx, nccl_api()->Broadcast(buf[0], buf[0], bytes / 8, ncclUint64, root, cm->nccl, ctx->stream));
+    LSP_NCCL(ctx, nccl_api()->Broadcast(buf[0], buf[0], bytes / 8, ncclUint64, root, ((ncclComm_t)cm->nccl), ctx->stream));
     return LSP_OK;
 }
 
@@ -140,7 +131,7 @@ int coll_allreduce_sum(lsp_comm* cm, const std::vector<int>& ranks, const std::v
         dev_free(ctx, (void*)d_srcs);
         return LSP_OK;
     }
-    LSP_NCCL(ctx, nccl_api()->AllReduce(buf[0], buf[0], bytes / 8, ncclUint64, ncclSum, cm->nccl, ctx->stream));
+    LSP_NCCL(ctx, nccl_api()->AllReduce(buf[0], buf[0], bytes / 8, ncclUint64, ncclSum, ((ncclComm_t)cm->nccl), ctx->stream));
     return LSP_OK;
 }
 
@@ -183,6 +174,7 @@ struct ShardTree {
     const Fr* top;    // 2G - 1 digests: layer 0 = the G subtree roots
     uint32_t log_h;   // global height
 };
+constexpr int LSP_MAX_FRI_ROUNDS = 32;   // log2 of the LDE height <= 31
 struct FriRoundS {
     const Fr* vec;    // round input: local slice (sharded) or the whole vector (replicated)
     ShardTree tree;   // for replicated rounds: local = the full tree, top unused
@@ -196,7 +188,7 @@ struct QueryArgsS {
     const Fr* quot_lde; int q;
     ShardTree quot_tree;
     int log_l;
-    const FriRoundS* rounds; int n_rounds;
+    FriRoundS rounds[LSP_MAX_FRI_ROUNDS]; int n_rounds;   // by value: no staging copy, no host synchronisation
     Fr* out; size_t per_query;
 };
 
@@ -246,7 +238,7 @@ __global__ void __launch_bounds__(128) k_query_gather_s(const __grid_constant__ 
         if (shard_sibling(A.quot_tree, k, index, rank, log_g, v)) fr_store(out + o + k, v);
     o += A.log_l;
     for (int r = 0; r < A.n_rounds; r++) {
-        const FriRoundS R = A.rounds[r];
+        const FriRoundS& R = A.rounds[r];
         const size_t index_i = index >> r;
         const int log_h = int(R.tree.log_h);  // pairs
         if (R.sharded) {
@@ -308,7 +300,6 @@ struct RankState {
     Fr* inv_den[2] = {nullptr, nullptr};
     Fr *folded = nullptr, *fri_dig = nullptr, *fri_top = nullptr, *tail = nullptr, *tail_dig = nullptr;
     uint32_t* idx = nullptr;
-    FriRoundS* rounds_dev = nullptr;
     std::vector<FriRoundS> rounds;
 };
 
@@ -342,7 +333,7 @@ extern "C" int lsp_comm_init_nccl(lsp_ctx* ctx, int rank, int world, const uint8
     cm->rank = rank;
     ncclUniqueId id;
     memcpy(&id, unique_id, 128);
-    ncclResult_t r = a->CommInitRank(&cm->nccl, world, id, rank);
+    ncclResult_t r = a->CommInitRank((ncclComm_t*)&cm->nccl, world, id, rank);
     if (r != ncclSuccess) {
         delete cm;
         return set_err(ctx, LSP_ERR_COMM, "ncclCommInitRank: %s", a->GetErrorString ? a->GetErrorString(r) : "error");
@@ -363,7 +354,7 @@ extern "C" int lsp_comm_init_local(lsp_ctx* ctx, int world, lsp_comm** out) {
 
 extern "C" void lsp_comm_destroy(lsp_comm* cm) {
     if (!cm) return;
-    if (cm->nccl && nccl_api()) nccl_api()->CommDestroy(cm->nccl);
+    if (((ncclComm_t)cm->nccl) && nccl_api()) nccl_api()->CommDestroy(((ncclComm_t)cm->nccl));
     cudaFree(cm->up_stage);
     cudaFree(cm->up_mat);
     delete cm;
@@ -379,7 +370,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     const size_t n = tr->rows, W = tr->width;
     if (!is_pow2(n)) return set_err(ctx, LSP_ERR_PARAM, "trace height %zu is not a power of two (prove would panic)", n);
     const int G = cm->world, log_g = ilog2(size_t(G));
-    const int log_n = ilog2(n), log_q = lsp_air_log_quotient_degree(n_lookups, n_cfgs), q = 1 << log_q;
+    const int log_n = ilog2(n), log_q = lsp_air_log_quotient_degree_cfg(lookups, n_lookups, cfgs, n_cfgs), q = 1 << log_q;
     const int log_b = int(fri->log_blowup), log_l = log_n + log_b;
     if (log_q > log_b) return set_err(ctx, LSP_ERR_PARAM, "quotient degree 2^%d exceeds blowup 2^%d", log_q, log_b);
     if (log_g > log_b) return set_err(ctx, LSP_ERR_PARAM, "%d ranks need at least %d cosets (log_blowup >= %d)", G, G, log_g);
@@ -496,14 +487,14 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_TRY(challenger_observe_dev(ctx, R.ch, R.sc + S_PUB0, 2));
         LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_ALPHA));
         LSP_TRY(P.get(&R.chunks, size_t(q) * n * 32));
-        // row block b of the quotient domain (b < q) holds chunk bitrev(b); its owner computes it
-        for (int b = 0; b < q; b++) {
-            if (b / Bs != R.rank) continue;
-            LSP_TRY(quotient_permutation_range(ctx, R.lde_t + size_t(b % Bs) * n, Lr, size_t(b) * n, log_n, log_q, cfg_dev, R.sc + S_PUB0,
-                                               R.sc + S_ALPHA, size_t(b) * n, n, R.chunks));
-        }
+        // row block b of the quotient domain (b < q) holds chunk bitrev(b); its owner computes it (the blocks of one
+        // rank are adjacent: one launch)
+        const int b0 = R.rank * Bs, b1 = std::min(q, b0 + Bs);
+        if (b0 < b1)
+            LSP_TRY(quotient_permutation_range(ctx, R.lde_t, Lr, size_t(b0) * n, log_n, log_q, cfg_dev, R.sc + S_PUB0, R.sc + S_ALPHA,
+                                               size_t(b0) * n, size_t(b1 - b0) * n, R.chunks));
     }
-    for (int b = 0; b < q; b++) {  // the one bulk exchange: N field elements per chunk
+    for (int b = 0; b < q && G > 1; b++) {  // the one bulk exchange: N field elements per chunk
         const int c = int(bitrev_host(uint32_t(b), log_q));
         const int owner = b / Bs;
         std::vector<void*> buf(H);
@@ -615,16 +606,18 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         const size_t local = len >> log_g;
         std::vector<const void*> send(H);
         std::vector<void*> recv(H);
-        for (size_t i = 0; i < H; i++) {
-            LSP_TRY(P.get(&st[i].tail, 2 * len * 32));
-            LSP_TRY(P.get(&st[i].tail_dig, 2 * len * 32));
-            send[i] = cur[i];
-            recv[i] = st[i].tail;
-        }
-        if (G > 1)
+        if (G > 1) {
+            for (size_t i = 0; i < H; i++) {
+                LSP_TRY(P.get(&st[i].tail, 2 * len * 32));
+                LSP_TRY(P.get(&st[i].tail_dig, 2 * len * 32));
+                send[i] = cur[i];
+                recv[i] = st[i].tail;
+            }
             LSP_TRY(coll_allgather(cm, ranks, send, recv, local * 32));
-        else
-            LSP_CUDA(ctx, cudaMemcpyAsync(st[0].tail, cur[0], len * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {  // one rank: nothing to gather, the rounds continue in place
+            st[0].tail = cur[0];
+            st[0].tail_dig = dig[0];
+        }
         for (size_t i = 0; i < H; i++) {
             RankState& R = st[i];
             Fr* c = R.tail;
@@ -662,14 +655,6 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_TRY(challenger_grind(ctx, R.ch, int(fri->proof_of_work_bits), p_pow));
         LSP_TRY(P.get(&R.idx, fri->num_queries * 4));
         LSP_TRY(challenger_sample_bits(ctx, R.ch, log_l, int(fri->num_queries), R.idx));
-        LSP_TRY(P.get(&R.rounds_dev, (n_rounds ? n_rounds : 1) * sizeof(FriRoundS)));
-        if (n_rounds) {
-            if (size_t(n_rounds) * sizeof(FriRoundS) > ctx->pinned_bytes) return set_err(ctx, LSP_ERR_PARAM, "too many FRI rounds");
-            LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // pinned staging buffer is shared
-            memcpy(ctx->pinned, R.rounds.data(), n_rounds * sizeof(FriRoundS));
-            LSP_CUDA(ctx, cudaMemcpyAsync(R.rounds_dev, ctx->pinned, n_rounds * sizeof(FriRoundS), cudaMemcpyHostToDevice, ctx->stream));
-            LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        }
         QueryArgsS A;
         A.idx = R.idx;
         A.rank = R.rank;
@@ -682,7 +667,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         A.q = q;
         A.quot_tree = ShardTree{R.dig_q, R.top_q, uint32_t(log_l)};
         A.log_l = log_l;
-        A.rounds = R.rounds_dev;
+        for (int rr = 0; rr < n_rounds; rr++) A.rounds[rr] = R.rounds[rr];
         A.n_rounds = n_rounds;
         A.out = R.proof + hdr_elems;
         A.per_query = per_query;
@@ -705,7 +690,9 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     LSP_CUDA(ctx, cudaMemcpyAsync(proof_out, out_dev, proof_elems * 32, cudaMemcpyDeviceToHost, ctx->stream));
     mark();  // 8
     ctx->phase = "";
+    LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, &st[0].ch->overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
     LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (*(volatile int*)ctx->pinned) return set_err(ctx, LSP_ERR_STATE, "challenger input buffer overflow");
     if (timings_ms_out)
         for (int i = 0; i < 8; i++) cudaEventElapsedTime(&timings_ms_out[i], ev[i], ev[i + 1]);
     return LSP_OK;

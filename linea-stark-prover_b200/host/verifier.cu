@@ -287,7 +287,7 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     if (!ctx || !fri || !publics || !proof_words_in || n_lookups < 0 || n_cfgs < 0 || n_lookups + n_cfgs <= 0) return LSP_ERR_PARAM;
     if ((n_cfgs && !cfgs) || (n_lookups && !lookups)) return LSP_ERR_PARAM;
     if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
-    const int log_q = lsp_air_log_quotient_degree(n_lookups, n_cfgs), q = 1 << log_q;
+    const int log_q = lsp_air_log_quotient_degree_cfg(lookups, n_lookups, cfgs, n_cfgs), q = 1 << log_q;
     const int log_b = int(fri->log_blowup), log_l = int(log_n) + log_b;
     if (log_l > 31 || log_l < 1) return set_err(ctx, LSP_ERR_PARAM, "LDE of 2^%d rows unsupported", log_l);
     if (fri->log_final_poly_len > log_n) return set_err(ctx, LSP_ERR_PARAM, "log_final_poly_len exceeds log2 of the trace height");

@@ -673,6 +673,24 @@ int lsp_oracle_verify(const fri_cfg* fri, uint32_t log_n, size_t width, const ai
 }
 
 /* ---- witness generation (trace/src/permutation.rs:24-93, trace/src/lib.rs:94-106) ----------- */
+/* columns 2c (inverse) and 2c+1 (running product) of a row-major N x (2c+2) matrix whose a/b columns are filled */
+static int witness_columns(fr* out, size_t n, uint32_t c, fr alpha, fr delta) {
+    size_t W = 2 * (size_t)c + 2;
+    /* per-row inversion, as the reference does (:70); the row loop is split so the
+       inversions can use every core, the running product stays sequential (:72) */
+    #pragma omp parallel for schedule(static)
+    for (size_t i = 0; i < n; i++) {
+        fr ac = ZERO, bc = ZERO;
+        for (uint32_t j = 0; j < c; j++) { ac = fr_add(fr_mul(ac, alpha), out[i * W + j]); bc = fr_add(fr_mul(bc, alpha), out[i * W + c + j]); }
+        fr bi = fr_inv(fr_add(bc, delta));
+        out[i * W + 2 * c] = bi;
+        out[i * W + 2 * c + 1] = fr_mul(fr_add(ac, delta), bi);
+    }
+    fr prev = ONE;
+    for (size_t i = 0; i < n; i++) { prev = fr_mul(prev, out[i * W + 2 * c + 1]); out[i * W + 2 * c + 1] = prev; }
+    return fr_eq(prev, ONE) ? 0 : -2;                 /* permutation.rs:76-79 */
+}
+
 /* seed -> alpha, delta, c columns a, b = rows of a shuffled; out: row-major N x (2c+2), Montgomery */
 int lsp_oracle_gen_trace(uint64_t seed, uint32_t c, uint32_t log_n, uint64_t* publics_out, uint64_t* trace_out) {
     init_consts();
@@ -687,19 +705,21 @@ int lsp_oracle_gen_trace(uint64_t seed, uint32_t c, uint32_t log_n, uint64_t* pu
     for (size_t i = n - 1; i > 0; i--) { size_t j = rng_u64(&g) % (i + 1); size_t t = perm[i]; perm[i] = perm[j]; perm[j] = t; }
     for (size_t i = 0; i < n; i++) for (uint32_t j = 0; j < c; j++) out[i * W + c + j] = out[perm[i] * W + j];
     free(perm);
-    /* per-row inversion, as the reference does (:70); the row loop is split so the
-       inversions can use every core, the running product stays sequential (:72) */
+    return witness_columns(out, n, c, alpha, delta);
+}
+
+/* `RawPermutationTrace::get_trace` + `RawTrace::get_trace` on given input columns: ab_rm is row-major
+   rows x 2c (a columns first), Montgomery limbs; publics = [alpha, delta]; out: row-major rows x (2c+2). */
+int lsp_oracle_permutation_trace(const uint64_t* ab_rm, size_t rows, uint32_t c, const uint64_t* publics, uint64_t* trace_out) {
+    init_consts();
+    size_t W = 2 * (size_t)c + 2;
+    fr alpha, delta;
+    memcpy(&alpha, publics, 32); memcpy(&delta, publics + 4, 32);
+    fr* out = (fr*)trace_out;
+    const fr* in = (const fr*)ab_rm;
     #pragma omp parallel for schedule(static)
-    for (size_t i = 0; i < n; i++) {
-        fr ac = ZERO, bc = ZERO;
-        for (uint32_t j = 0; j < c; j++) { ac = fr_add(fr_mul(ac, alpha), out[i * W + j]); bc = fr_add(fr_mul(bc, alpha), out[i * W + c + j]); }
-        fr bi = fr_inv(fr_add(bc, delta));
-        out[i * W + 2 * c] = bi;
-        out[i * W + 2 * c + 1] = fr_mul(fr_add(ac, delta), bi);
-    }
-    fr prev = ONE;
-    for (size_t i = 0; i < n; i++) { prev = fr_mul(prev, out[i * W + 2 * c + 1]); out[i * W + 2 * c + 1] = prev; }
-    return fr_eq(prev, ONE) ? 0 : -2;                 /* permutation.rs:76-79 */
+    for (size_t i = 0; i < rows; i++) for (uint32_t j = 0; j < 2 * c; j++) out[i * W + j] = in[i * 2 * c + j];
+    return witness_columns(out, rows, c, alpha, delta);
 }
 
 /* n <= 0: one thread per online processor, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1). */

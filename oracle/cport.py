@@ -43,6 +43,7 @@ def load():
         lib.lsp_oracle_verify.argtypes = [C.POINTER(FriCfg), C.c_uint32, C.c_size_t, C.POINTER(AirCfg), C.c_int, u64p,
                                           u64p, C.c_size_t]
         lib.lsp_oracle_gen_trace.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]
+        lib.lsp_oracle_permutation_trace.argtypes = [u64p, C.c_size_t, C.c_uint32, u64p, u64p]
         lib.lsp_oracle_set_lookups.argtypes = [C.POINTER(C.c_uint32), C.c_int]
         _lib = lib
     return _lib
@@ -154,6 +155,17 @@ def gen_trace(seed: int, c: int, log_n: int):
     if rc != 0:
         raise RuntimeError(f"lsp_oracle_gen_trace failed: {rc}")
     return pub, tr, n, w
+
+
+def permutation_trace(ab_limbs: np.ndarray, n: int, c: int, publics_limbs: np.ndarray) -> np.ndarray:
+    """Witness of the permutation argument (trace/src/permutation.rs:24-93) from given a/b columns:
+    ab_limbs uint64[n*2c,4] row-major Montgomery -> trace uint64[n*(2c+2),4]."""
+    tr = np.zeros((n * (2 * c + 2), 4), dtype=np.uint64)
+    rc = load().lsp_oracle_permutation_trace(_p(np.ascontiguousarray(ab_limbs)), n, c,
+                                             _p(np.ascontiguousarray(publics_limbs)), _p(tr))
+    if rc != 0:
+        raise RuntimeError(f"lsp_oracle_permutation_trace failed: {rc} (b is not a permutation of a)")
+    return tr
 
 
 def threads() -> int:

@@ -8,7 +8,7 @@ import sys
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent.parent
-ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--cpu-budget", "1", "--log-n", "10"]
+ARGS = ["--impl", "reference", "--steps", "1", "--warmup", "0", "--log-n", "10"]
 
 
 def _run(extra_env=None, extra_args=()):
@@ -34,6 +34,14 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["unit"] == "s" and cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # the arm proves the workload it names, in full: nothing sampled, nothing scaled
+    assert "scaled" not in cb["sample"] and "2^10-row" in cb["sample"]
+    assert len(d["parity"]["fnv1a64"]) == 16 and d["parity"]["verified_by_cpu_port"] is True
+
+
+def test_reference_arm_proves_the_same_seeded_trace_every_time():
+    a, b = json.loads(_run().strip()), json.loads(_run().strip())
+    assert a["parity"]["fnv1a64"] == b["parity"]["fnv1a64"]
 
 
 def test_reference_arm_config_equals_our_arms_config():
