@@ -75,6 +75,18 @@ int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s);
 int lsp_set_poseidon2(lsp_ctx* ctx, int width, int sbox_d, int rounds_f, int rounds_p,
                       const uint64_t* constants, const uint64_t* internal_diag_m1);
 
+/* Field parameters fixed by the fork-only `p3-bls12-377-fr` crate, which is not available to check:
+ * `Bls12_377Fr::GENERATOR` (the coset shift of every LDE `TwoAdicFriPcs` commits: `Val::GENERATOR / domain.shift`)
+ * and `two_adic_generator(47)` (every smaller root is a power of it), both as Montgomery limbs.  Defaults:
+ * arkworks' FrConfig values, GENERATOR = 22 and TWO_ADIC_ROOT_OF_UNITY = 22^((r-1)/2^47).  The call validates
+ * them (non-zero generator outside every two-adic subgroup, primitive 2^47-th root) and drops the cached tables. */
+int lsp_set_field_consts(lsp_ctx* ctx, const uint64_t generator[4], const uint64_t two_adic_root_2_47[4]);
+/* Transcript order of `TwoAdicFriPcs::open`.  alpha_before_openings != 0: the batching challenge
+ * is sampled before the opened values are computed; observe_opened_values != 0: the opened values (trace at zeta,
+ * trace at zeta*g, every quotient chunk at zeta) are observed by the challenger.  The pinned fork is (1, 0) -- the
+ * default; upstream Plonky3 after early 2025 is (0, 1).  Applies to prove, sharded prove and verify alike. */
+int lsp_set_transcript_flags(lsp_ctx* ctx, int alpha_before_openings, int observe_opened_values);
+
 /* ---- parity probes (SURVEY.md section 4 tier 3) --------------------------- */
 /* Elementwise Fr ops on host arrays: op 0 add, 1 sub, 2 mul, 3 inverse (b unused),
  * 4 halve (b unused).  Replaces ark-ff `Fp256` arithmetic behind `Val` (bin/src/config.rs:9). */
@@ -184,6 +196,11 @@ int lsp_cbor_permutation_decode(const uint8_t* cbor, size_t len, uint8_t* be_row
  * scan on all host threads for files in serde's regular layout (~4 GB/s on 16 cores), serial otherwise. */
 int lsp_cbor_permutation_read(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_cols, char* name, size_t name_cap,
                               uint8_t** be_rowmajor_out);
+/* `RawTrace::push_traces` (trace/src/lib.rs:62-79) resizes every sub-trace to the tallest one before its witness is built
+ * (`resize`, permutation.rs:134-142: zero rows).  `_decode` therefore accepts any `rows` >= the file's own height, and
+ * `_read_rows` allocates max(min_rows, height) rows; the rows past the file's height are zero (filters included). */
+int lsp_cbor_permutation_read_rows(const uint8_t* cbor, size_t len, size_t min_rows, size_t* rows, uint32_t* n_cols, char* name,
+                                   size_t name_cap, uint8_t** be_rowmajor_out);
 void lsp_host_free(void* p);
 /* Process-wide switch: after lsp_host_pinned(1) the `_read` functions hand out PAGE-LOCKED buffers (portable across the
  * process's devices), recycled through a small pool on lsp_host_free, so that `lsp_*_trace_be` uploads at PCIe rate and
@@ -199,6 +216,8 @@ int lsp_cbor_lookup_decode(const uint8_t* cbor, size_t len, uint8_t* be_rowmajor
                            uint32_t n_tables, uint32_t n_b_cols);
 int lsp_cbor_lookup_read(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_a_cols, uint32_t* n_tables,
                          uint32_t* n_b_cols, char* name, size_t name_cap, uint8_t** be_rowmajor_out);
+int lsp_cbor_lookup_read_rows(const uint8_t* cbor, size_t len, size_t min_rows, size_t* rows, uint32_t* n_a_cols, uint32_t* n_tables,
+                              uint32_t* n_b_cols, char* name, size_t name_cap, uint8_t** be_rowmajor_out);
 /* `get_columns` (`from_be_bytes_mod_order`, :95-118) + `get_trace` (:24-93) on the device: like
  * lsp_permutation_trace, from raw 32-byte big-endian values (any value < 2^256, reduced mod r). */
 int lsp_permutation_trace_be(lsp_ctx* ctx, const uint8_t* be_rowmajor, size_t rows, uint32_t n_cols,

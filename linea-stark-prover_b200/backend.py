@@ -142,6 +142,16 @@ class Context:
         self.check(self.lib.lsp_set_poseidon2(self.h, 3, sbox_d, rounds_f, rounds_p, ffi.as_u64p(c), ffi.as_u64p(d)),
                    "lsp_set_poseidon2")
 
+    def set_field_consts(self, generator: int, two_adic_root_2_47: int):
+        """`Bls12_377Fr::GENERATOR` and `two_adic_generator(47)` (canonical ints): lsp_set_field_consts."""
+        g, w = to_mont_array([generator]), to_mont_array([two_adic_root_2_47])
+        self.check(self.lib.lsp_set_field_consts(self.h, ffi.as_u64p(g), ffi.as_u64p(w)), "lsp_set_field_consts")
+
+    def set_transcript_flags(self, alpha_before_openings: bool = True, observe_opened_values: bool = False):
+        """Transcript order of `TwoAdicFriPcs::open`: lsp_set_transcript_flags (pinned fork: True, False)."""
+        self.check(self.lib.lsp_set_transcript_flags(self.h, int(alpha_before_openings), int(observe_opened_values)),
+                   "lsp_set_transcript_flags")
+
     # -- parity probes ----------------------------------------------------------
     def fr_op(self, op: str, a, b=None):
         code = {"add": 0, "sub": 1, "mul": 2, "inv": 3, "halve": 4}[op]
@@ -353,15 +363,18 @@ def _c_cfgs(cfgs):
     return arr, keep
 
 
-def read_raw_permutation_trace(blob: bytes, _fill=None):
+def read_raw_permutation_trace(blob: bytes, _fill=None, rows_target=None):
     """`RawPermutationTrace::read_file` (trace/src/permutation.rs:17-22) through the library's CBOR parser
     (host-only entry points: no GPU needed).  Returns (be_bytes uint8[rows*2c*32], rows, n_cols, name).
-    The decoder writes every byte of the output (values and zero padding); `_fill` lets a test poison it first."""
+    The decoder writes every byte of the output (values and zero padding); `_fill` lets a test poison it first.
+    `rows_target` >= the file's height is `push_traces`' resize to the tallest input (trace/src/lib.rs:62-79)."""
     lib = ffi.load()
     rows, nc = C.c_size_t(), C.c_uint32()
     name = C.create_string_buffer(256)
     if lib.lsp_cbor_permutation_shape(blob, len(blob), C.byref(rows), C.byref(nc), name, 256) != 0:
         raise BackendError("not a CBOR RawPermutationTrace")
+    if rows_target is not None:
+        rows = C.c_size_t(rows_target)
     out = np.empty(rows.value * 2 * nc.value * 32, dtype=np.uint8)
     if _fill is not None:
         out[:] = _fill
@@ -370,7 +383,7 @@ def read_raw_permutation_trace(blob: bytes, _fill=None):
     return out, rows.value, nc.value, name.value.decode()
 
 
-def read_raw_lookup_trace(blob: bytes, _fill=None):
+def read_raw_lookup_trace(blob: bytes, _fill=None, rows_target=None):
     """`RawLookupTrace::read_file` (trace/src/lookup.rs:20-44) through the library's CBOR parser (host only).
     Returns (be_bytes uint8[rows*(n_a + T*n_b + 1 + T)*32], rows, n_a, n_tables, n_b, name)."""
     lib = ffi.load()
@@ -379,6 +392,8 @@ def read_raw_lookup_trace(blob: bytes, _fill=None):
     if lib.lsp_cbor_lookup_shape(blob, len(blob), C.byref(rows), C.byref(na), C.byref(nt), C.byref(nb), name, 256) != 0:
         raise BackendError("not a CBOR RawLookupTrace")
     stride = na.value + nt.value * nb.value + 1 + nt.value
+    if rows_target is not None:
+        rows = C.c_size_t(rows_target)
     out = np.empty(rows.value * stride * 32, dtype=np.uint8)
     if _fill is not None:
         out[:] = _fill
@@ -532,10 +547,10 @@ def prove(ctx: Context, fri: FriConfig, cfgs, trace, publics, timings=None):
     if n & (n - 1) or n == 0:
         raise BackendError(f"trace height {n} is not a power of two")
     log_n = n.bit_length() - 1
-    log_q = int(ctx.lib.lsp_air_log_quotient_degree(n_l, n_p))
+    log_q = int(ctx.lib.lsp_air_log_quotient_degree_cfg(larr, n_l, arr, n_p))
     words = int(ctx.lib.lsp_proof_words(log_n, w, log_q, C.byref(cf)))
     if words == 0:
-        raise BackendError("unsupported FRI parameters for this trace height")
+        words = 4   # unsupported FRI parameters for this height: the call below refuses them and says why
     out = np.empty(words, dtype=np.uint64)
     if n_l == 0:      # the permutation-only entry points (the benchmarked path)
         if isinstance(trace, Mat):
@@ -623,7 +638,7 @@ def quotient_permutation(ctx: Context, lde: Mat, log_n: int, log_q: int, cfgs, p
 def quotient_air(ctx: Context, lde: Mat, log_n: int, cfgs, publics, alpha) -> Mat:
     """`quotient_values` for a `LineaAIR` with lookup and permutation configs; N x q, q from the AIR's degree."""
     larr, n_l, arr, n_p, keep = _c_air_cfgs(cfgs)
-    log_q = int(ctx.lib.lsp_air_log_quotient_degree(n_l, n_p))
+    log_q = int(ctx.lib.lsp_air_log_quotient_degree_cfg(larr, n_l, arr, n_p))
     pub = to_mont_array(publics)
     al = to_mont_array([alpha])
     h = C.c_void_p()
@@ -708,10 +723,10 @@ def prove_sharded(comm: Comm, fri: FriConfig, cfgs, trace, publics, timings=None
     if n & (n - 1) or n == 0:
         raise BackendError(f"trace height {n} is not a power of two")
     log_n = n.bit_length() - 1
-    log_q = int(ctx.lib.lsp_air_log_quotient_degree(n_l, n_p))
+    log_q = int(ctx.lib.lsp_air_log_quotient_degree_cfg(larr, n_l, arr, n_p))
     words = int(ctx.lib.lsp_proof_words(log_n, w, log_q, C.byref(cf)))
     if words == 0:
-        raise BackendError("unsupported FRI parameters for this trace height")
+        words = 4   # unsupported FRI parameters for this height: the call below refuses them and says why
     out = np.empty(words, dtype=np.uint64)
     if isinstance(trace, Mat):
         rc = ctx.lib.lsp_prove_air_sharded_dev(comm.h, C.byref(cf), trace.h, larr, n_l, arr, n_p, ffi.as_u64p(pub),

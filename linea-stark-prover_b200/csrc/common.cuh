@@ -14,6 +14,12 @@
 
 namespace lsp {
 struct TwiddleCache;
+// Field parameters the fork-only `p3-bls12-377-fr` crate fixes: Montgomery form, device resident.
+struct FieldConsts {
+    Fr gen;      // Val::GENERATOR: the coset shift of TwoAdicFriPcs
+    Fr gen_inv;  // 1 / gen
+    Fr root47;   // two_adic_generator(47)
+};
 }
 
 struct lsp_ctx {
@@ -23,6 +29,11 @@ struct lsp_ctx {
     std::string err;
     bool p2_set = false;
     lsp::P2Params p2;
+    lsp::FieldConsts* fc = nullptr;      // device memory; lsp_set_field_consts
+    // TwoAdicFriPcs::open of the pinned fork samples the batching challenge BEFORE computing the opened values and never
+    // observes them; later upstream observes them first.  lsp_set_transcript_flags selects either.
+    bool alpha_before_openings = true;
+    bool observe_opened_values = false;
     uint64_t launches = 0;
     // omega_{2^k}^j tables, j < 2^(k-1), forward and inverse, keyed by k
     std::map<int, lsp::Fr*> tw_fwd, tw_inv;

@@ -161,7 +161,81 @@ __global__ void k_gather_siblings(const Fr* __restrict__ digests, size_t h, int 
 // ---------------------------------------------------------------------------
 // context
 // ---------------------------------------------------------------------------
+static bool limbs_reduced(const uint64_t* l) {
+    static const uint64_t P[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
+    for (int i = 3; i >= 0; i--) {
+        if (l[i] < P[i]) return true;
+        if (l[i] > P[i]) return false;
+    }
+    return false;
+}
+
 extern "C" int lsp_abi_version(void) { return LSP_ABI_VERSION; }
+
+// Validates and completes the field parameters: gen != 0 with gen^(2^31) != 1 (its cosets of every supported two-adic
+// subgroup are disjoint from the subgroup: L <= 2^31), root^(2^46) == -1 (a primitive 2^47-th root of unity), and
+// fills gen_inv.  status: 0 ok, 1 bad generator, 2 bad root.
+__global__ void k_field_consts_setup(FieldConsts* fc, int* status) {
+    const Fr g = fr_load(&fc->gen), w = fr_load(&fc->root47);
+    int st = 0;
+    Fr t = g;
+    for (int i = 0; i < 31; i++) t = fr_sqr(t);
+    if (fr_is_zero(g) || fr_eq(t, fr_one())) st = 1;
+    t = w;
+    for (int i = 0; i < 46; i++) t = fr_sqr(t);
+    if (!fr_eq(t, fr_neg(fr_one()))) st = st ? st : 2;
+    fr_store(&fc->gen_inv, fr_inv(g));
+    *status = st;
+}
+
+static void drop_shape_caches(lsp_ctx* ctx) {  // everything derived from the field parameters
+    for (auto& kv : ctx->tw_fwd) cudaFree(kv.second);
+    for (auto& kv : ctx->tw_inv) cudaFree(kv.second);
+    ctx->tw_fwd.clear();
+    ctx->tw_inv.clear();
+    for (auto& kv : ctx->quot_sel) {
+        cudaFree(kv.second.scal);
+        cudaFree(kv.second.inv0);
+        cudaFree(kv.second.inv1);
+    }
+    ctx->quot_sel.clear();
+}
+
+// `Val::GENERATOR` and `Val::two_adic_generator(47)` (fork-only `p3-bls12-377-fr`), Montgomery limbs.
+extern "C" int lsp_set_field_consts(lsp_ctx* ctx, const uint64_t generator[4], const uint64_t two_adic_root_2_47[4]) {
+    if (!ctx || !generator || !two_adic_root_2_47) return LSP_ERR_PARAM;
+    if (!limbs_reduced(generator) || !limbs_reduced(two_adic_root_2_47)) return set_err(ctx, LSP_ERR_PARAM, "field constant is not reduced");
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FieldConsts old;
+    LSP_CUDA(ctx, cudaMemcpy(&old, ctx->fc, sizeof old, cudaMemcpyDeviceToHost));
+    FieldConsts h;
+    memset(&h, 0, sizeof h);
+    memcpy(&h.gen, generator, 32);
+    memcpy(&h.root47, two_adic_root_2_47, 32);
+    int* status = nullptr;
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&status, 4));
+    LSP_CUDA(ctx, cudaMemcpyAsync(ctx->fc, &h, sizeof h, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_LAUNCH(ctx, k_field_consts_setup, 1, 1, 0, ctx->fc, status);
+    LSP_CUDA(ctx, cudaMemcpyAsync(ctx->pinned, status, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const int st = *(volatile int*)ctx->pinned;
+    if (st != 0) {
+        LSP_CUDA(ctx, cudaMemcpy(ctx->fc, &old, sizeof old, cudaMemcpyHostToDevice));
+        return set_err(ctx, LSP_ERR_PARAM, st == 1 ? "generator is zero or lies in a two-adic subgroup" : "not a primitive 2^47-th root of unity");
+    }
+    drop_shape_caches(ctx);  // twiddles and selector tables were built from the old parameters
+    return LSP_OK;
+}
+
+// Transcript order of `TwoAdicFriPcs::open`.  The pinned fork: (1, 0).  Later upstream: (0, 1).
+extern "C" int lsp_set_transcript_flags(lsp_ctx* ctx, int alpha_before_openings, int observe_opened_values) {
+    if (!ctx) return LSP_ERR_PARAM;
+    ctx->alpha_before_openings = alpha_before_openings != 0;
+    ctx->observe_opened_values = observe_opened_values != 0;
+    return LSP_OK;
+}
 
 extern "C" int lsp_ctx_create(int device, lsp_ctx** out) {
     if (!out) return LSP_ERR_PARAM;
@@ -188,6 +262,19 @@ extern "C" int lsp_ctx_create(int device, lsp_ctx** out) {
         delete ctx;
         return LSP_ERR_NOMEM;
     }
+    // field parameters: arkworks' FrConfig values until lsp_set_field_consts says otherwise
+    int rc = cudaMalloc((void**)&ctx->fc, sizeof(FieldConsts)) == cudaSuccess ? LSP_OK : LSP_ERR_NOMEM;
+    if (rc == LSP_OK) {
+        uint64_t g[4], w[4];
+        memcpy(g, FR_GEN_DEFAULT, 32);
+        memcpy(w, FR_ROOT47_DEFAULT, 32);
+        cudaMemset(ctx->fc, 0, sizeof(FieldConsts));
+        rc = lsp_set_field_consts(ctx, g, w);
+    }
+    if (rc != LSP_OK) {
+        lsp_ctx_destroy(ctx);
+        return rc;
+    }
     *out = ctx;
     return LSP_OK;
 }
@@ -196,8 +283,8 @@ extern "C" void lsp_ctx_destroy(lsp_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& kv : ctx->tw_fwd) cudaFree(kv.second);
-    for (auto& kv : ctx->tw_inv) cudaFree(kv.second);
+    drop_shape_caches(ctx);
+    cudaFree(ctx->fc);
     for (auto& r : ctx->timing_recs) {
         cudaEventDestroy(r.e0);
         cudaEventDestroy(r.e1);
@@ -205,11 +292,6 @@ extern "C" void lsp_ctx_destroy(lsp_ctx* ctx) {
     for (auto& e : ctx->ev_pool) cudaEventDestroy(e);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaFree(ctx->grid_barrier);
-    for (auto& kv : ctx->quot_sel) {
-        cudaFree(kv.second.scal);
-        cudaFree(kv.second.inv0);
-        cudaFree(kv.second.inv1);
-    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -355,15 +437,6 @@ extern "C" int lsp_int_peak(lsp_ctx* ctx, double* mac32_per_s) {
     for (int i = 1; i < LSP_INT_PEAK_FORMS; i++)
         if (v[i] > *mac32_per_s) *mac32_per_s = v[i];
     return LSP_OK;
-}
-
-static bool limbs_reduced(const uint64_t* l) {
-    static const uint64_t P[4] = {0x0a11800000000001ull, 0x59aa76fed0000001ull, 0x60b44d1e5c37b001ull, 0x12ab655e9a2ca556ull};
-    for (int i = 3; i >= 0; i--) {
-        if (l[i] < P[i]) return true;
-        if (l[i] > P[i]) return false;
-    }
-    return false;
 }
 
 extern "C" int lsp_set_poseidon2(lsp_ctx* ctx, int width, int sbox_d, int rounds_f, int rounds_p,

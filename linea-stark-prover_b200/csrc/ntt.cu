@@ -23,9 +23,9 @@ namespace lsp {
 constexpr int NTT_MAX_T = 10;  // 2^10 elements = 32 KiB of shared memory per tile
 
 // tw[j] = w^j (or w^-j) for j < n/2, w = omega_{2^log_n}
-__global__ void __launch_bounds__(128) k_gen_twiddles(Fr* __restrict__ tw, int log_n, int inverse) {
+__global__ void __launch_bounds__(128) k_gen_twiddles(const FieldConsts* __restrict__ fc, Fr* __restrict__ tw, int log_n, int inverse) {
     size_t half = (size_t(1) << log_n) >> 1;
-    Fr w = fr_two_adic_generator(log_n);
+    Fr w = fr_two_adic_generator(fc, log_n);
     for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < half; j += size_t(gridDim.x) * blockDim.x) {
         uint32_t e = inverse ? uint32_t(((size_t(1) << log_n) - j) & ((size_t(1) << log_n) - 1)) : uint32_t(j);
         fr_store(tw + j, fr_pow_u32(w, e));
@@ -35,13 +35,13 @@ __global__ void __launch_bounds__(128) k_gen_twiddles(Fr* __restrict__ tw, int l
 // Two-level power tables of the coset bases S_c = shift * w_L^c, c < 2^added_bits:
 //   lo[c][j] = S_c^j            j < 2^lo_bits
 //   hi[c][j] = S_c^(j<<lo_bits) j < 2^(log_n - lo_bits)
-__global__ void __launch_bounds__(128) k_coset_pow_tables(Fr* __restrict__ lo, Fr* __restrict__ hi, const Fr* __restrict__ shift, int log_n,
+__global__ void __launch_bounds__(128) k_coset_pow_tables(const FieldConsts* __restrict__ fc, Fr* __restrict__ lo, Fr* __restrict__ hi, const Fr* __restrict__ shift, int log_n,
                                                           int added_bits, int lo_bits, int block0) {
     // destination row block (block0 + blockIdx.y) of the bit-reversed LDE holds coset bitrev(block)
     int c = blockIdx.y;
     int log_l = log_n + added_bits;
     uint32_t coset = bitrev32(uint32_t(block0 + c), added_bits);
-    Fr base = fr_mul(fr_load(shift), fr_pow_u32(fr_two_adic_generator(log_l), coset));
+    Fr base = fr_mul(fr_load(shift), fr_pow_u32(fr_two_adic_generator(fc, log_l), coset));
     size_t n_lo = size_t(1) << lo_bits, n_hi = size_t(1) << (log_n - lo_bits);
     for (size_t j = blockIdx.x * size_t(blockDim.x) + threadIdx.x; j < n_lo + n_hi; j += size_t(gridDim.x) * blockDim.x) {
         if (j < n_lo)
@@ -165,7 +165,7 @@ int twiddles(lsp_ctx* ctx, int log_n, bool inverse, const Fr** out) {
     size_t half = (size_t(1) << log_n) >> 1;
     Fr* tw = nullptr;
     LSP_CUDA(ctx, cudaMalloc(&tw, half * 32));
-    LSP_LAUNCH(ctx, k_gen_twiddles, grid_for(ctx, half, 128), 128, 0, tw, log_n, inverse ? 1 : 0);
+    LSP_LAUNCH(ctx, k_gen_twiddles, grid_for(ctx, half, 128), 128, 0, (const FieldConsts*)ctx->fc, tw, log_n, inverse ? 1 : 0);
     cache[log_n] = tw;
     *out = tw;
     return LSP_OK;
@@ -245,7 +245,7 @@ int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width
     LSP_TRY(tmp.get((void**)&pow_hi, n_blocks * n_hi * 32));
     {
         dim3 grid((unsigned)((n_lo + n_hi + 127) / 128), (unsigned)n_blocks);
-        LSP_LAUNCH(ctx, k_coset_pow_tables, grid, 128, 0, pow_lo, pow_hi, shift, log_n, added_bits, lo_bits, block0);
+        LSP_LAUNCH(ctx, k_coset_pow_tables, grid, 128, 0, (const FieldConsts*)ctx->fc, pow_lo, pow_hi, shift, log_n, added_bits, lo_bits, block0);
     }
     std::vector<int> ts;
     split_passes(log_n, ts);

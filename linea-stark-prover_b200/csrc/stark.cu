@@ -162,7 +162,9 @@ __global__ void __launch_bounds__(32) k_verify_transcript(const __grid_constant_
     sample_to(A.scal + VT_ALPHA);
     observe(A.quot_commit, 1);
     sample_to(A.scal + VT_ZETA);
-    sample_to(A.scal + VT_ALPHA_FRI);                       // (fork-era order) batching challenge before the betas
+    if (A.alpha_before_openings) sample_to(A.scal + VT_ALPHA_FRI);   // fork-era order: batching challenge first, values never observed
+    if (A.observe_opened_values) observe(A.opened, A.n_opened);
+    if (!A.alpha_before_openings) sample_to(A.scal + VT_ALPHA_FRI);
     for (int r = 0; r < A.n_rounds; r++) {
         observe(A.fri_commits + r, 1);
         sample_to(A.betas + r);
@@ -319,10 +321,10 @@ struct InvDenScalars {
     Fr e0;                    // g^-1 / (1 - u[0])   (the g^-1 makes E the inverse of g*w - z directly)
 };
 
-__global__ void k_invden_setup(const Fr* __restrict__ z, int m, InvDenScalars* __restrict__ out) {
+__global__ void k_invden_setup(const FieldConsts* __restrict__ fc, const Fr* __restrict__ z, int m, InvDenScalars* __restrict__ out) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= gridDim.x * blockDim.x) return;
-    Fr ginv = fr_const(FR_GEN_INV);
+    Fr ginv = fr_load(&fc->gen_inv);
     Fr u = fr_mul(fr_load(z + p), ginv);
     InvDenScalars* o = out + p;
     o->u[m] = u;
@@ -386,7 +388,7 @@ int inverse_denominators_range(lsp_ctx* ctx, const Fr* z_dev, int n_points, int 
     InvDenScalars* S = nullptr;
     Scratch tmp(ctx);
     LSP_TRY(tmp.get((void**)&S, sizeof(InvDenScalars) * n_points));
-    LSP_LAUNCH(ctx, k_invden_setup, 1, n_points, 0, z_dev, log_m, S);
+    LSP_LAUNCH(ctx, k_invden_setup, 1, n_points, 0, (const FieldConsts*)ctx->fc, z_dev, log_m, S);
     int la = log_m < 10 ? log_m : 10;
     int lb = log_m - 3 > la ? log_m - 3 : la;
     const int depth = log_m - lb;
@@ -430,25 +432,26 @@ struct QuotientArgs {
     const Fr* zh;         // per chunk c: Z_H = g^N * w_q^c - 1, then 1/Z_H   (2q entries)
     const Fr* tw_nq;      // omega_{Nq}^j, j < Nq/2
     const Fr* w_n_inv;    // omega_N^-1
+    const FieldConsts* fc;
     Fr* chunks;           // q columns of N
     size_t p0, count;     // storage rows [p0, p0+count) handled by this launch; lde/inv_* are indexed by p - p_base
     size_t p_base;        // storage row that lde[0] / inv_first[0] correspond to
 };
 
-__global__ void k_quotient_setup(int log_n, int log_q, Fr* __restrict__ zh, Fr* __restrict__ w_n_inv, Fr* __restrict__ pts) {
+__global__ void k_quotient_setup(const FieldConsts* __restrict__ fc, int log_n, int log_q, Fr* __restrict__ zh, Fr* __restrict__ w_n_inv, Fr* __restrict__ pts) {
     int c = threadIdx.x;
     int q = 1 << log_q;
     if (c < q) {
-        Fr g = fr_const(FR_GEN);
+        Fr g = fr_load(&fc->gen);
         Fr gn = g;
         for (int i = 0; i < log_n; i++) gn = fr_sqr(gn);
-        Fr wq = fr_pow_u32(fr_two_adic_generator(log_q), uint32_t(c));
+        Fr wq = fr_pow_u32(fr_two_adic_generator(fc, log_q), uint32_t(c));
         Fr z = fr_sub(fr_mul(gn, wq), fr_one());
         fr_store(zh + c, z);
         fr_store(zh + q + c, fr_inv(z));
     }
     if (c == 0) {
-        Fr w = fr_two_adic_generator(log_n);
+        Fr w = fr_two_adic_generator(fc, log_n);
         Fr wi = fr_pow_u32(w, uint32_t((size_t(1) << log_n) - 1));  // w^(N-1) = w^-1
         fr_store(w_n_inv, wi);
         fr_store(pts, fr_one());      // selector points: 1 and w_N^-1
@@ -462,6 +465,7 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
     const uint32_t q = 1u << A.log_q;
     const Fr alpha_air = fr_load(A.publics), delta = fr_load(A.publics + 1), alpha = fr_load(A.alpha);
     const Fr w_n_inv = fr_load(A.w_n_inv);
+    const Fr gen = fr_load(&A.fc->gen);
     const Fr one = fr_one();
     for (size_t pi = blockIdx.x * size_t(blockDim.x) + threadIdx.x; pi < A.count; pi += size_t(gridDim.x) * blockDim.x) {
         const size_t pg = A.p0 + pi;                 // global storage row
@@ -473,7 +477,7 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
         // x = g * w_{Nq}^i
         Fr wi = (i < nq / 2) ? fr_load_nc(A.tw_nq + i) : fr_neg(fr_load_nc(A.tw_nq + (i - nq / 2)));
         if (nq == 1) wi = one;
-        Fr x = fr_mul(fr_const(FR_GEN), wi);
+        Fr x = fr_mul(gen, wi);
         Fr zh = fr_load_nc(A.zh + c), zh_inv = fr_load_nc(A.zh + q + c);
         Fr is_first = fr_mul(zh, fr_load_nc(A.inv_first + p));
         Fr is_last = fr_mul(zh, fr_load_nc(A.inv_last + p));
@@ -508,7 +512,7 @@ int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, siz
         LSP_CUDA(ctx, cudaMalloc((void**)&sel.inv0, count * 32));
         LSP_CUDA(ctx, cudaMalloc((void**)&sel.inv1, count * 32));
         Fr* zh0 = sel.scal;
-        LSP_LAUNCH(ctx, k_quotient_setup, 1, unsigned(q < 32 ? 32 : q), 0, log_n, log_q, zh0, zh0 + 2 * q, zh0 + 2 * q + 1);
+        LSP_LAUNCH(ctx, k_quotient_setup, 1, unsigned(q < 32 ? 32 : q), 0, (const FieldConsts*)ctx->fc, log_n, log_q, zh0, zh0 + 2 * q, zh0 + 2 * q + 1);
         Fr* inv01[2] = {sel.inv0, sel.inv1};
         LSP_TRY(inverse_denominators_range(ctx, zh0 + 2 * q + 1, 2, lnq, p0, count, inv01));
         it = ctx->quot_sel.emplace(key, sel).first;
@@ -531,6 +535,7 @@ int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, siz
     A.zh = zh;
     A.tw_nq = tw;
     A.w_n_inv = w_n_inv;
+    A.fc = ctx->fc;
     A.chunks = chunks;
     A.p0 = p0;
     A.count = count;

@@ -4,11 +4,7 @@
 
 namespace lsp {
 
-// GENERATOR = 22 and its inverse, 1/2 (Montgomery form)
-__device__ __constant__ const uint32_t FR_GEN[8] = {0xfffffed3u, 0x296c7fffu, 0x6ffffec7u, 0x92921665u,
-                                                    0x92860e69u, 0x4c01534du, 0xb9819970u, 0x0c79cfc4u};
-__device__ __constant__ const uint32_t FR_GEN_INV[8] = {0xd1745d17u, 0xb76f9745u, 0xafffffffu, 0xfed18274u,
-                                                        0x5b36a173u, 0xfce61983u, 0x78dc8d16u, 0x068b6ffdu};
+// 1/2 (Montgomery form)
 __device__ __constant__ const uint32_t FR_HALF[8] = {0xfffffffau, 0xc396ffffu, 0x1ffffff9u, 0xe6013607u,
                                                      0xd6b1dff7u, 0xbbc63149u, 0x62f41ff9u, 0x0ffb9fc8u};
 
@@ -19,14 +15,15 @@ __device__ __forceinline__ Fr fr_const(const uint32_t* c) {
     return r;
 }
 
-// TWO_ADIC_ROOT_OF_UNITY = 22^((r-1)/2^47), Montgomery form (ark-bls12-377 FrConfig)
-__device__ __constant__ const uint32_t FR_ROOT47[8] = {0xda3ad648u, 0xaf80da4du, 0xfc381dacu, 0x5e223adbu,
-                                                       0xb2f92525u, 0x03ba0666u, 0x3befb0ceu, 0x0f906c5bu};
+// `Bls12_377Fr::GENERATOR` (the coset shift of every committed LDE) and `two_adic_generator(47)`: the fork-only crate that
+// fixes them is unavailable, so they are run-time parameters of the context (lsp_set_field_consts),
+// resident in device memory; the defaults are arkworks' FrConfig values (GENERATOR = 22, TWO_ADIC_ROOT_OF_UNITY).
+// (FieldConsts itself is declared in common.cuh.)
+constexpr uint32_t FR_GEN_DEFAULT[8] = {0xfffffed3u, 0x296c7fffu, 0x6ffffec7u, 0x92921665u, 0x92860e69u, 0x4c01534du, 0xb9819970u, 0x0c79cfc4u};
+constexpr uint32_t FR_ROOT47_DEFAULT[8] = {0xda3ad648u, 0xaf80da4du, 0xfc381dacu, 0x5e223adbu, 0xb2f92525u, 0x03ba0666u, 0x3befb0ceu, 0x0f906c5bu};
 
-__device__ __forceinline__ Fr fr_two_adic_generator(int bits) {
-    Fr w;
-#pragma unroll
-    for (int i = 0; i < 8; i++) w.l[i] = FR_ROOT47[i];
+__device__ __forceinline__ Fr fr_two_adic_generator(const FieldConsts* fc, int bits) {
+    Fr w = fr_load(&fc->root47);
     for (int i = bits; i < 47; i++) w = fr_sqr(w);
     return w;
 }
@@ -76,6 +73,27 @@ struct DevChallenger {  // HashChallenger<Val,Hash,1> state, resident in device 
     int n_input;
     int overflow;
 };
+
+// `FriConfig` (bin/src/main.rs:58-64) against a trace of 2^log_n rows and 2^log_q quotient chunks: the one place the
+// prover, the sharded prover and the verifier check it.
+//  * log_final_poly_len >= log_n would leave ZERO commit-phase rounds: the reduced opening only enters the fold chain
+//    inside a round, so the low-degree test would check nothing about the committed data (the pinned verifier then
+//    rejects every honest proof with FinalPolyMismatch and accepts a forged all-zero final polynomial).  Refused.
+//  * proof_of_work_bits > 32: `sample_bits` reads the low limb of the canonical integer; more bits than that would
+//    silently be enforced as 32.  Refused.
+inline int check_fri_config(lsp_ctx* ctx, const lsp_fri_config* fri, int log_n, int log_q) {
+    const int log_b = int(fri->log_blowup), log_l = log_n + log_b;
+    if (log_q > log_b) return set_err(ctx, LSP_ERR_PARAM, "quotient degree 2^%d exceeds blowup 2^%d", log_q, log_b);
+    if (log_l > 31 || log_l < 1) return set_err(ctx, LSP_ERR_PARAM, "LDE of 2^%d rows unsupported", log_l);
+    if (int(fri->log_final_poly_len) >= log_n)
+        return set_err(ctx, LSP_ERR_PARAM, "log_final_poly_len %u leaves no commit-phase round for a trace of 2^%d rows (vacuous low-degree test)",
+                       fri->log_final_poly_len, log_n);
+    if (fri->num_queries == 0 || fri->num_queries > 4096) return set_err(ctx, LSP_ERR_PARAM, "num_queries out of range");
+    if (fri->proof_of_work_bits > 32) return set_err(ctx, LSP_ERR_PARAM, "proof_of_work_bits %u > 32 unsupported", fri->proof_of_work_bits);
+    if ((size_t(1) << (log_b + int(fri->log_final_poly_len))) + 8 > size_t(CH_CAP))
+        return set_err(ctx, LSP_ERR_PARAM, "final polynomial of 2^%d coefficients unsupported", log_b + int(fri->log_final_poly_len));
+    return LSP_OK;
+}
 
 struct PermCfgDev {  // flattened LineaAIR config list in device memory: lookups first, then permutations
     // lookup i lives at lk + lk_off[i]:
@@ -181,7 +199,8 @@ __device__ __forceinline__ Fr fold_air_constraints(const PermCfgDev& cfg, const 
 enum { VT_ALPHA = 0, VT_ZETA = 1, VT_ALPHA_FRI = 2, VT_COUNT = 3 };
 struct VerifyTranscriptArgs {
     int log_n, n_rounds, n_final, pow_bits, log_l, n_queries;
-    const Fr *trace_commit, *quot_commit, *publics, *fri_commits, *final_poly, *pow_witness;
+    int alpha_before_openings, observe_opened_values, n_opened;   // lsp_set_transcript_flags; opened values: 2W + q
+    const Fr *trace_commit, *quot_commit, *publics, *opened, *fri_commits, *final_poly, *pow_witness;
     Fr *scal, *betas;
     uint32_t *pow_low, *idx;
 };

@@ -56,6 +56,8 @@ SIGNATURES = {
     "lsp_int_peaks": (C.c_int, [vp, C.POINTER(C.c_double)]),
     "lsp_permutation_trace": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, u64p, C.POINTER(vp)]),
     "lsp_set_poseidon2": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, u64p, u64p]),
+    "lsp_set_field_consts": (C.c_int, [vp, u64p, u64p]),
+    "lsp_set_transcript_flags": (C.c_int, [vp, C.c_int, C.c_int]),
     "lsp_fr_op": (C.c_int, [vp, C.c_int, u64p, u64p, u64p, C.c_size_t]),
     "lsp_poseidon2_permute": (C.c_int, [vp, u64p, u64p, C.c_size_t]),
     "lsp_hash_rows": (C.c_int, [vp, u64p, C.c_size_t, C.c_size_t, u64p]),
@@ -98,6 +100,10 @@ SIGNATURES = {
                                             C.POINTER(C.c_void_p)]),
     "lsp_cbor_lookup_read": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                        C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "lsp_cbor_permutation_read_rows": (C.c_int, [C.c_char_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32), C.c_char_p,
+                                                 C.c_size_t, C.POINTER(C.c_void_p)]),
+    "lsp_cbor_lookup_read_rows": (C.c_int, [C.c_char_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_char_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "lsp_host_free": (None, [C.c_void_p]),
     "lsp_host_pinned": (C.c_int, [C.c_int]),
     "lsp_lookup_trace": (C.c_int, [vp, u64p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.POINTER(vp)]),

@@ -123,8 +123,14 @@ struct Reader {
     bool at_break() { return need(1) && *p == 0xff; }
     void skip_break() { p++; }
 
-    // Skips one complete item of any type.
-    void skip() {
+    // Skips one complete item of any type.  Nesting (arrays, maps, tags) is bounded like ciborium's recursion limit
+    // (256): a longer run of 0x81 / 0xc0 / 0x9f bytes under an unknown key is a malformed file, not a stack overflow.
+    static constexpr int MAX_DEPTH = 256;
+    void skip(int depth = 0) {
+        if (depth > MAX_DEPTH) {
+            ok = false;
+            return;
+        }
         uint64_t arg;
         bool indef;
         int m = head(arg, indef);
@@ -133,7 +139,7 @@ struct Reader {
             case 0: case 1: case 7: break;
             case 2: case 3:
                 if (indef) {
-                    while (ok && !at_break()) skip();
+                    while (ok && !at_break()) skip(depth + 1);
                     if (ok) skip_break();
                 } else if (need(arg)) {
                     p += arg;
@@ -142,14 +148,14 @@ struct Reader {
             case 4: case 5: {
                 uint64_t n = m == 5 ? 2 * arg : arg;
                 if (indef) {
-                    while (ok && !at_break()) skip();
+                    while (ok && !at_break()) skip(depth + 1);
                     if (ok) skip_break();
                 } else {
-                    for (uint64_t i = 0; ok && i < n; i++) skip();
+                    for (uint64_t i = 0; ok && i < n; i++) skip(depth + 1);
                 }
                 break;
             }
-            case 6: skip(); break;
+            case 6: skip(depth + 1); break;
             default: ok = false;
         }
     }
@@ -685,17 +691,22 @@ extern "C" int lsp_cbor_lookup_decode(const uint8_t* cbor, size_t len, uint8_t* 
     LookupShape s;
     std::vector<Run> runs;
     if (!lookup_shape(cbor, len, s, &runs)) return LSP_ERR_PARAM;
-    if (s.height() != rows || s.a_rows.size() != n_a_cols || s.b_rows.size() != n_tables || s.b_rows[0].size() != n_b_cols) return LSP_ERR_PARAM;
+    if (s.height() > rows || s.a_rows.size() != n_a_cols || s.b_rows.size() != n_tables || s.b_rows[0].size() != n_b_cols) return LSP_ERR_PARAM;
     return fill_lookup(cbor, len, s, runs, be_rowmajor, rows) ? LSP_OK : LSP_ERR_PARAM;
 }
 
 extern "C" int lsp_cbor_lookup_read(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_a_cols, uint32_t* n_tables,
                                     uint32_t* n_b_cols, char* name, size_t name_cap, uint8_t** be_rowmajor_out) {
+    return lsp_cbor_lookup_read_rows(cbor, len, 0, rows, n_a_cols, n_tables, n_b_cols, name, name_cap, be_rowmajor_out);
+}
+
+extern "C" int lsp_cbor_lookup_read_rows(const uint8_t* cbor, size_t len, size_t min_rows, size_t* rows, uint32_t* n_a_cols,
+                                         uint32_t* n_tables, uint32_t* n_b_cols, char* name, size_t name_cap, uint8_t** be_rowmajor_out) {
     if (!cbor || !rows || !n_a_cols || !n_tables || !n_b_cols || !be_rowmajor_out) return LSP_ERR_PARAM;
     LookupShape s;
     std::vector<Run> runs;
     if (!lookup_shape(cbor, len, s, &runs) || s.height() == 0) return LSP_ERR_PARAM;
-    const size_t h = s.height(), stride = s.a_rows.size() + s.b_rows.size() * (s.b_rows[0].size() + 1) + 1;
+    const size_t h = s.height() > min_rows ? s.height() : min_rows, stride = s.a_rows.size() + s.b_rows.size() * (s.b_rows[0].size() + 1) + 1;
     uint8_t* out = static_cast<uint8_t*>(host_alloc(h * stride * 32));
     if (!out) return LSP_ERR_NOMEM;
     if (!fill_lookup(cbor, len, s, runs, out, h)) {
@@ -727,17 +738,22 @@ extern "C" int lsp_cbor_permutation_decode(const uint8_t* cbor, size_t len, uint
     Shape s;
     std::vector<Run> runs;
     if (!permutation_shape(cbor, len, s, &runs)) return LSP_ERR_PARAM;
-    if (s.a_rows.size() != n_cols || s.height() != rows) return LSP_ERR_PARAM;
+    if (s.a_rows.size() != n_cols || s.height() > rows) return LSP_ERR_PARAM;
     return fill_permutation(cbor, len, s, runs, be_rowmajor, rows) ? LSP_OK : LSP_ERR_PARAM;
 }
 
 extern "C" int lsp_cbor_permutation_read(const uint8_t* cbor, size_t len, size_t* rows, uint32_t* n_cols, char* name, size_t name_cap,
                                          uint8_t** be_rowmajor_out) {
+    return lsp_cbor_permutation_read_rows(cbor, len, 0, rows, n_cols, name, name_cap, be_rowmajor_out);
+}
+
+extern "C" int lsp_cbor_permutation_read_rows(const uint8_t* cbor, size_t len, size_t min_rows, size_t* rows, uint32_t* n_cols, char* name,
+                                              size_t name_cap, uint8_t** be_rowmajor_out) {
     if (!cbor || !rows || !n_cols || !be_rowmajor_out) return LSP_ERR_PARAM;
     Shape s;
     std::vector<Run> runs;
     if (!permutation_shape(cbor, len, s, &runs) || s.height() == 0) return LSP_ERR_PARAM;
-    const size_t h = s.height(), nc = s.a_rows.size();
+    const size_t h = s.height() > min_rows ? s.height() : min_rows, nc = s.a_rows.size();
     uint8_t* out = static_cast<uint8_t*>(host_alloc(h * 2 * nc * 32));
     if (!out) return LSP_ERR_NOMEM;
     if (!fill_permutation(cbor, len, s, runs, out, h)) {

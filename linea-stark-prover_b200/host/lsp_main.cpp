@@ -17,6 +17,7 @@
 //             [--pow-bits 0] [--sbox-d 5] [--device 0] [--gpus 1] [--out proof.bin] [--repeat 1]
 //   --gpus N: ONE proof sharded over devices device..device+N-1 (one host thread and one lsp_ctx per GPU, NCCL
 //   between them: lsp_prove_air_sharded_dev); every rank builds the witness on its own device from the same parsed bytes.
+#include <algorithm>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -231,6 +232,24 @@ int main(int argc, char** argv) {
         double t_read = 0, t_cbor = 0;
         size_t cbor_bytes = 0;
         std::vector<SubTrace> subs;
+        // `push_traces` (trace/src/lib.rs:62-79): the trace height is the tallest column of ANY input file, and every
+        // sub-trace is resized to it (zero rows) before its witness is built.  With one file its own height is that
+        // height; with several a shape pass over each finds the maximum first.
+        size_t max_height = 0;
+        if (lookups.size() + perms.size() > 1) {
+            auto shape = [&](const std::string& path, bool is_lookup) {
+                MappedFile blob(path);
+                size_t rows = 0;
+                uint32_t a = 0, t = 0, b = 0;
+                if (is_lookup)
+                    CHECK(ctx, lsp_cbor_lookup_shape(blob.data(), blob.size(), &rows, &a, &t, &b, nullptr, 0));
+                else
+                    CHECK(ctx, lsp_cbor_permutation_shape(blob.data(), blob.size(), &rows, &a, nullptr, 0));
+                max_height = std::max(max_height, rows);
+            };
+            for (auto& f : lookups) shape(f, true);
+            for (auto& f : perms) shape(f, false);
+        }
         auto load = [&](const std::string& path, bool is_lookup) {
             clk::time_point t0 = clk::now();
             MappedFile blob(path);
@@ -241,9 +260,9 @@ int main(int argc, char** argv) {
             char name[128] = {0};
             t0 = clk::now();
             if (is_lookup)
-                CHECK(ctx, lsp_cbor_lookup_read(blob.data(), blob.size(), &st.rows, &st.na, &st.nt, &st.nb, name, sizeof name, &st.be));
+                CHECK(ctx, lsp_cbor_lookup_read_rows(blob.data(), blob.size(), max_height, &st.rows, &st.na, &st.nt, &st.nb, name, sizeof name, &st.be));
             else
-                CHECK(ctx, lsp_cbor_permutation_read(blob.data(), blob.size(), &st.rows, &st.na, name, sizeof name, &st.be));
+                CHECK(ctx, lsp_cbor_permutation_read_rows(blob.data(), blob.size(), max_height, &st.rows, &st.na, name, sizeof name, &st.be));
             t_cbor += ms_since(t0);
             st.name = name;
             subs.push_back(st);
@@ -265,8 +284,8 @@ int main(int argc, char** argv) {
         uint32_t col = 0;
         size_t height = 0, li = 0, pi = 0;
         for (const SubTrace& st : subs) {
-            if (height && st.rows != height) {
-                fprintf(stderr, "all sub-traces must have one height (%zu != %zu)\n", st.rows, height);
+            if (height && st.rows != height) {  // cannot happen: every file was read at the common height
+                fprintf(stderr, "internal error: sub-trace heights differ (%zu != %zu)\n", st.rows, height);
                 return 1;
             }
             height = st.rows;
@@ -326,7 +345,7 @@ int main(int argc, char** argv) {
         // ---- prove (main.rs:80-86)
         int log_n = 0;
         while ((size_t(1) << log_n) < height) log_n++;
-        int log_q = lsp_air_log_quotient_degree(int(lcfg.size()), int(pcfg.size()));
+        int log_q = lsp_air_log_quotient_degree_cfg(lcfg.data(), int(lcfg.size()), pcfg.data(), int(pcfg.size()));
         size_t words = lsp_proof_words(uint32_t(log_n), col, uint32_t(log_q), &fri);
         std::vector<std::vector<uint64_t>> proofs(ranks.size(), std::vector<uint64_t>(words));
         std::vector<uint64_t>& proof = proofs[0];

@@ -27,11 +27,11 @@ __global__ void k_open_scalars(const Fr* __restrict__ alpha, const Fr* __restric
 }
 
 // final_poly = idft(bit_reverse(folded)); F <= 1024 values, one thread per coefficient.
-__global__ void k_final_poly(const Fr* __restrict__ folded, int log_f, Fr scale /* 1/F */, Fr* __restrict__ out) {
+__global__ void k_final_poly(const FieldConsts* __restrict__ fc, const Fr* __restrict__ folded, int log_f, Fr scale /* 1/F */, Fr* __restrict__ out) {
     int k = threadIdx.x;
     int f = 1 << log_f;
     if (k >= f) return;
-    Fr w = fr_two_adic_generator(log_f);
+    Fr w = fr_two_adic_generator(fc, log_f);
     Fr wk = fr_pow_u32(w, uint32_t((f - k) & (f - 1)));  // w^-k
     Fr acc = fr_zero(), wp = fr_one();
     for (int j = 0; j < f; j++) {

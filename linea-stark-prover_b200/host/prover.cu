@@ -106,7 +106,7 @@ extern "C" int lsp_air_log_quotient_degree(int n_lookups, int n_perms) {
 }
 
 extern "C" size_t lsp_proof_words(uint32_t log_n, uint32_t width, uint32_t log_q, const lsp_fri_config* fri) {
-    if (!fri || fri->log_final_poly_len > log_n) return 0;
+    if (!fri || fri->log_final_poly_len >= log_n) return 0;   // zero commit-phase rounds: refused (check_fri_config)
     size_t log_l = size_t(log_n) + fri->log_blowup;
     size_t q = size_t(1) << log_q;
     size_t rounds = log_n - fri->log_final_poly_len;

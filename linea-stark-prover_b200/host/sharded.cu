@@ -136,17 +136,17 @@ int coll_allreduce_sum(lsp_comm* cm, const std::vector<int>& ranks, const std::v
 }
 
 // ---- device helpers --------------------------------------------------------------------------
-__global__ void k_chunk_consts(const Fr* __restrict__ zeta, int log_n, int log_q, Fr* __restrict__ shifts, Fr* __restrict__ zeta_next,
+__global__ void k_chunk_consts(const FieldConsts* __restrict__ fc, const Fr* __restrict__ zeta, int log_n, int log_q, Fr* __restrict__ shifts, Fr* __restrict__ zeta_next,
                                Fr* __restrict__ chunk_pts) {
     int c = threadIdx.x;
     int lnq = log_n + log_q;
     if (c < (1 << log_q)) {
         uint32_t e = uint32_t(((size_t(1) << lnq) - size_t(c)) & ((size_t(1) << lnq) - 1));
-        Fr wi = fr_pow_u32(fr_two_adic_generator(lnq), e);  // w_{Nq}^-c
+        Fr wi = fr_pow_u32(fr_two_adic_generator(fc, lnq), e);  // w_{Nq}^-c
         if (shifts) fr_store(shifts + c, wi);
-        if (zeta) fr_store(chunk_pts + c, fr_mul(fr_mul(fr_load(zeta), fr_const(FR_GEN_INV)), wi));
+        if (zeta) fr_store(chunk_pts + c, fr_mul(fr_mul(fr_load(zeta), fr_load(&fc->gen_inv)), wi));
     }
-    if (c == 0 && zeta) fr_store(zeta_next, fr_mul(fr_load(zeta), fr_two_adic_generator(log_n)));
+    if (c == 0 && zeta) fr_store(zeta_next, fr_mul(fr_load(zeta), fr_two_adic_generator(fc, log_n)));
 }
 struct ReduceArgsS {
     const Fr* trace_lde; size_t rows; int width;
@@ -372,10 +372,8 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     const int G = cm->world, log_g = ilog2(size_t(G));
     const int log_n = ilog2(n), log_q = lsp_air_log_quotient_degree_cfg(lookups, n_lookups, cfgs, n_cfgs), q = 1 << log_q;
     const int log_b = int(fri->log_blowup), log_l = log_n + log_b;
-    if (log_q > log_b) return set_err(ctx, LSP_ERR_PARAM, "quotient degree 2^%d exceeds blowup 2^%d", log_q, log_b);
+    LSP_TRY(check_fri_config(ctx, fri, log_n, log_q));
     if (log_g > log_b) return set_err(ctx, LSP_ERR_PARAM, "%d ranks need at least %d cosets (log_blowup >= %d)", G, G, log_g);
-    if (int(fri->log_final_poly_len) > log_n || log_l > 31) return set_err(ctx, LSP_ERR_PARAM, "unsupported FRI shape");
-    if (fri->num_queries == 0 || fri->num_queries > 4096) return set_err(ctx, LSP_ERR_PARAM, "num_queries out of range");
     const size_t need = lsp_proof_words(log_n, uint32_t(W), log_q, fri);
     if (proof_words < need) return set_err(ctx, LSP_ERR_PARAM, "proof buffer too small: %zu < %zu words", proof_words, need);
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -443,7 +441,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_TRY(P.get(&R.sc, S_COUNT * 32));
         LSP_CUDA(ctx, cudaMemcpyAsync(R.sc + S_PUB0, publics, 64, cudaMemcpyHostToDevice, ctx->stream));
         LSP_LAUNCH(ctx, k_set_small, 1, 1, 0, R.sc + S_LOGN, uint32_t(log_n));
-        LSP_LAUNCH(ctx, k_set_small, 1, 1, 0, R.sc + S_GEN, 22u);
+        LSP_CUDA(ctx, cudaMemcpyAsync(R.sc + S_GEN, &ctx->fc->gen, 32, cudaMemcpyDeviceToDevice, ctx->stream));  // shift = GENERATOR / 1
         LSP_TRY(P.get(&R.ch, sizeof(DevChallenger)));
         LSP_TRY(challenger_init(ctx, R.ch));
         LSP_TRY(P.get(&R.proof, proof_elems * 32));
@@ -513,7 +511,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_TRY(P.get(&R.dig_q, (2 * Lr - 1) * 32));
         LSP_TRY(P.get(&R.top_q, 2 * size_t(G) * 32));
         LSP_TRY(P.get(&R.cols_q, q * sizeof(Fr*)));
-        LSP_LAUNCH(ctx, k_chunk_consts, 1, 32, 0, (const Fr*)nullptr, log_n, log_q, R.sc + S_CHUNK_SHIFT, (Fr*)nullptr, (Fr*)nullptr);
+        LSP_LAUNCH(ctx, k_chunk_consts, 1, 32, 0, (const FieldConsts*)ctx->fc, (const Fr*)nullptr, log_n, log_q, R.sc + S_CHUNK_SHIFT, (Fr*)nullptr, (Fr*)nullptr);
         LSP_TRY(interpolate_columns(ctx, R.chunks, n, q, R.coef_q));
         for (int c = 0; c < q; c++)
             LSP_TRY(coset_evaluate_blocks(ctx, R.coef_q + size_t(c) * n, n, 1, log_b, R.sc + S_CHUNK_SHIFT + c, R.rank * Bs, Bs,
@@ -532,11 +530,15 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         Fr* p_chunks = p_next + W;
         LSP_TRY(challenger_observe_dev(ctx, R.ch, R.proof + 1, 1));
         LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_ZETA));
-        LSP_LAUNCH(ctx, k_chunk_consts, 1, 32, 0, (const Fr*)(R.sc + S_ZETA), log_n, log_q, (Fr*)nullptr, R.sc + S_ZETA_NEXT, R.sc + S_CHUNK_PT);
-        LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_ALPHA_FRI));
+        LSP_LAUNCH(ctx, k_chunk_consts, 1, 32, 0, (const FieldConsts*)ctx->fc, (const Fr*)(R.sc + S_ZETA), log_n, log_q, (Fr*)nullptr, R.sc + S_ZETA_NEXT, R.sc + S_CHUNK_PT);
+        // `TwoAdicFriPcs::open`: the pinned fork samples the batching challenge first and never observes the opened
+        // values; later upstream observes them (trace at zeta, trace at zeta', each chunk at zeta) and samples after.
+        if (ctx->alpha_before_openings) LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_ALPHA_FRI));
         LSP_TRY(eval_columns_at(ctx, coef_t, n, W, R.sc + S_ZETA, p_local));
         LSP_TRY(eval_columns_at(ctx, coef_t, n, W, R.sc + S_ZETA_NEXT, p_next));
         for (int c = 0; c < q; c++) LSP_TRY(eval_columns_at(ctx, R.coef_q + size_t(c) * n, n, 1, R.sc + S_CHUNK_PT + c, p_chunks + c));
+        if (ctx->observe_opened_values) LSP_TRY(challenger_observe_dev(ctx, R.ch, p_local, int(2 * W + q)));
+        if (!ctx->alpha_before_openings) LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_ALPHA_FRI));
         LSP_LAUNCH(ctx, k_open_scalars, 1, 1, 0, R.sc + S_ALPHA_FRI, p_local, p_next, p_chunks, int(W), q, R.sc + S_OPEN);
         LSP_TRY(P.get(&R.inv_den[0], Lr * 32));
         LSP_TRY(P.get(&R.inv_den[1], Lr * 32));
@@ -640,7 +642,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
                 ln >>= 1;
             }
             Fr* p_final = R.proof + 2 + 2 * W + q + n_rounds;
-            LSP_LAUNCH(ctx, k_final_poly, 1, unsigned(ln < 32 ? 32 : ln), 0, (const Fr*)c, log_f, host_pow2_inverse(log_f), p_final);
+            LSP_LAUNCH(ctx, k_final_poly, 1, unsigned(ln < 32 ? 32 : ln), 0, (const FieldConsts*)ctx->fc, (const Fr*)c, log_f, host_pow2_inverse(log_f), p_final);
             LSP_TRY(challenger_observe_dev(ctx, R.ch, p_final, int(ln)));
         }
     }

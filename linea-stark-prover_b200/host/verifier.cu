@@ -95,6 +95,7 @@ struct VerifyArgs {
     int* status;   // n_queries x (4 + n_rounds): [index, final poly, trace path, quotient path, round paths...]
     int* ood_bad;
     PermCfgDev cfg;
+    const FieldConsts* fc;
 };
 constexpr int ST_INDEX = 0, ST_FINAL = 1, ST_TRACE = 2, ST_QUOT = 3, ST_ROUND = 4;
 
@@ -121,13 +122,13 @@ __device__ __forceinline__ void verify_fold_one(const VerifyArgs& A, int qi) {
     const Fr* trow = in + 1;
     const Fr* qrow = in + 1 + A.W + A.log_l;
     const Fr zeta = fr_load(A.scal + VT_ZETA), a = fr_load(A.scal + VT_ALPHA_FRI);
-    const Fr zeta_next = fr_mul(zeta, fr_two_adic_generator(A.log_n));
+    const Fr zeta_next = fr_mul(zeta, fr_two_adic_generator(A.fc, A.log_n));
     // s = w_L^bitrev(index): the queried point is x = g * s
-    const Fr wl = fr_two_adic_generator(A.log_l);
+    const Fr wl = fr_two_adic_generator(A.fc, A.log_l);
     const uint32_t e = bitrev32(index, A.log_l);
     Fr s = fr_pow_u32(wl, e);
     Fr s_inv = fr_pow_u32(wl, uint32_t(((size_t(1) << A.log_l) - e) & ((size_t(1) << A.log_l) - 1)));
-    const Fr x = fr_mul(fr_const(FR_GEN), s);
+    const Fr x = fr_mul(fr_load(&A.fc->gen), s);
     const Fr ix0 = fr_inv(fr_sub(x, zeta)), ix1 = fr_inv(fr_sub(x, zeta_next));
     Fr ap = fr_one(), ro = fr_zero();
     for (int c = 0; c < A.W; c++) {
@@ -226,10 +227,10 @@ __device__ __forceinline__ void verify_ood_block(const VerifyArgs& A) {
     const Fr one = fr_one();
     if (t < q * q && i != j) {
         const int lnq = A.log_n + A.log_q;
-        const Fr wnq = fr_two_adic_generator(lnq);
+        const Fr wnq = fr_two_adic_generator(A.fc, lnq);
         const uint32_t mask = uint32_t((size_t(1) << lnq) - 1);
         // shift_k = g * w_{Nq}^k:  zeta / shift_j = zeta * g^-1 * w^-j,   shift_i / shift_j = w^(i-j)
-        Fr a = fr_mul(fr_mul(zeta, fr_const(FR_GEN_INV)), fr_pow_u32(wnq, (0u - uint32_t(j)) & mask));
+        Fr a = fr_mul(fr_mul(zeta, fr_load(&A.fc->gen_inv)), fr_pow_u32(wnq, (0u - uint32_t(j)) & mask));
         Fr b = fr_pow_u32(wnq, (uint32_t(i) - uint32_t(j)) & mask);
         for (int k = 0; k < A.log_n; k++) {
             a = fr_sqr(a);
@@ -238,7 +239,7 @@ __device__ __forceinline__ void verify_ood_block(const VerifyArgs& A) {
         factor[t] = fr_mul(fr_sub(a, one), fr_inv(fr_sub(b, one)));
     }
     if (t >= 64 && t < 67) {
-        const Fr wn_inv = fr_pow_u32(fr_two_adic_generator(A.log_n), uint32_t((size_t(1) << A.log_n) - 1));
+        const Fr wn_inv = fr_pow_u32(fr_two_adic_generator(A.fc, A.log_n), uint32_t((size_t(1) << A.log_n) - 1));
         Fr v;
         if (t == 64) v = fr_sub(zeta, one);
         else if (t == 65) v = fr_sub(zeta, wn_inv);
@@ -261,7 +262,7 @@ __device__ __forceinline__ void verify_ood_block(const VerifyArgs& A) {
     Fr zn = zeta;
     for (int k = 0; k < A.log_n; k++) zn = fr_sqr(zn);
     const Fr z_h = fr_sub(zn, one);
-    const Fr wn_inv = fr_pow_u32(fr_two_adic_generator(A.log_n), uint32_t((size_t(1) << A.log_n) - 1));
+    const Fr wn_inv = fr_pow_u32(fr_two_adic_generator(A.fc, A.log_n), uint32_t((size_t(1) << A.log_n) - 1));
     const Fr is_first = fr_mul(z_h, inv3[0]);
     const Fr is_last = fr_mul(z_h, inv3[1]);
     const Fr is_trans = fr_sub(zeta, wn_inv);
@@ -289,11 +290,8 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     if (!ctx->p2_set) return set_err(ctx, LSP_ERR_STATE, "lsp_set_poseidon2 has not been called");
     const int log_q = lsp_air_log_quotient_degree_cfg(lookups, n_lookups, cfgs, n_cfgs), q = 1 << log_q;
     const int log_b = int(fri->log_blowup), log_l = int(log_n) + log_b;
-    if (log_l > 31 || log_l < 1) return set_err(ctx, LSP_ERR_PARAM, "LDE of 2^%d rows unsupported", log_l);
-    if (fri->log_final_poly_len > log_n) return set_err(ctx, LSP_ERR_PARAM, "log_final_poly_len exceeds log2 of the trace height");
-    if (fri->num_queries == 0 || fri->num_queries > 4096) return set_err(ctx, LSP_ERR_PARAM, "num_queries out of range");
+    LSP_TRY(check_fri_config(ctx, fri, int(log_n), log_q));
     const int n_rounds = int(log_n) - int(fri->log_final_poly_len), log_f = log_b + int(fri->log_final_poly_len);
-    if ((size_t(1) << log_f) + 8 > size_t(CH_CAP)) return set_err(ctx, LSP_ERR_PARAM, "final polynomial of 2^%d coefficients unsupported", log_f);
     // the proof's shape is a function of the parameters: any other length is InvalidProofShape
     if (proof_words != lsp_proof_words(log_n, uint32_t(width), uint32_t(log_q), fri)) return LSP_VERIFY_INVALID_PROOF_SHAPE;
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -351,6 +349,7 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     A.scal = sc;
     A.betas = betas;
     A.idx = idx;
+    A.fc = ctx->fc;
     A.W = W;
     A.q = q;
     A.log_n = int(log_n);
@@ -376,6 +375,10 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     T.trace_commit = proof;
     T.quot_commit = proof + 1;
     T.publics = A.publics;
+    T.alpha_before_openings = ctx->alpha_before_openings ? 1 : 0;
+    T.observe_opened_values = ctx->observe_opened_values ? 1 : 0;
+    T.opened = A.p_local;
+    T.n_opened = 2 * W + q;
     T.fri_commits = A.p_commits;
     T.final_poly = A.p_final;
     T.pow_witness = p_pow;

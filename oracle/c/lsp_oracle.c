@@ -116,6 +116,19 @@ static void init_consts(void) {
     HALF = fr_halve(ONE);
     g_init = 1;
 }
+/* Parameters the fork-only crate fixes; the twins of lsp_set_field_consts / lsp_set_transcript_flags. */
+static int g_alpha_before_openings = 1, g_observe_opened_values = 0;
+int lsp_oracle_set_field_consts(const uint64_t* generator, const uint64_t* two_adic_root_2_47) {
+    init_consts();
+    fr g, w; memcpy(&g, generator, 32); memcpy(&w, two_adic_root_2_47, 32);
+    fr t = w; for (int i = 0; i < TWO_ADICITY - 1; i++) t = fr_sqr(t);
+    if (fr_is_zero(g) || !fr_eq(t, fr_neg(ONE))) return -1;
+    GEN = g; GEN_INV = fr_inv(g); ROOT47 = w;
+    return 0;
+}
+void lsp_oracle_set_transcript_flags(int alpha_before_openings, int observe_opened_values) {
+    g_alpha_before_openings = alpha_before_openings != 0; g_observe_opened_values = observe_opened_values != 0;
+}
 static fr two_adic_generator(int bits) { fr w = ROOT47; for (int i = bits; i < TWO_ADICITY; i++) w = fr_sqr(w); return w; }
 static inline uint32_t bitrev(uint32_t x, int bits) {
     uint32_t r = 0; for (int i = 0; i < bits; i++) { r = (r << 1) | (x & 1); x >>= 1; } return r;
@@ -498,8 +511,10 @@ int lsp_oracle_prove(const fri_cfg* fri, const uint64_t* trace_rm, size_t rows, 
     fr zeta = ch_sample(ch);
     fr zeta_next = fr_mul(zeta, two_adic_generator(log_n));
 
-    /* open: alpha first (fork-era), inverse denominators, barycentric openings, reduced rows */
-    fr a_fri = ch_sample(ch);
+    /* open: alpha first (fork-era; or after the observed openings, see g_alpha_before_openings), inverse denominators,
+       barycentric openings, reduced rows */
+    fr a_fri = ZERO;
+    if (g_alpha_before_openings) a_fri = ch_sample(ch);
     fr* fold_all = (fr*)malloc(2 * L * sizeof(fr));
     {
         fr wl = two_adic_generator(log_l);
@@ -511,6 +526,8 @@ int lsp_oracle_prove(const fri_cfg* fri, const uint64_t* trace_rm, size_t rows, 
         interpolate_coset_cols(cols_t, (int)W, log_n, zeta, p_local);
         interpolate_coset_cols(cols_t, (int)W, log_n, zeta_next, p_next);
         for (int c = 0; c < q; c++) interpolate_coset_cols(&cols_q[c], 1, log_n, zeta, p_chunks + c);
+        if (g_observe_opened_values) for (size_t i = 0; i < 2 * W + (size_t)q; i++) ch_observe(ch, p_local[i]);
+        if (!g_alpha_before_openings) a_fri = ch_sample(ch);
         fr ap[512]; ap[0] = ONE; for (size_t i = 1; i < 2 * W + q + 1; i++) ap[i] = fr_mul(ap[i - 1], a_fri);
         fr ry0 = ZERO, ry1 = ZERO; for (size_t i = 0; i < W; i++) { ry0 = fr_add(ry0, fr_mul(ap[i], p_local[i])); ry1 = fr_add(ry1, fr_mul(ap[i], p_next[i])); }
         #pragma omp parallel for schedule(static)
@@ -603,7 +620,10 @@ int lsp_oracle_verify(const fri_cfg* fri, uint32_t log_n, size_t width, const ai
     fr alpha = ch_sample(ch);
     ch_observe(ch, proof[1]);
     fr zeta = ch_sample(ch), zeta_next = fr_mul(zeta, two_adic_generator((int)log_n));
-    fr a_fri = ch_sample(ch);
+    fr a_fri = ZERO;
+    if (g_alpha_before_openings) a_fri = ch_sample(ch);
+    if (g_observe_opened_values) for (size_t i = 0; i < 2 * width + (size_t)q; i++) ch_observe(ch, p_local[i]);
+    if (!g_alpha_before_openings) a_fri = ch_sample(ch);
     fr betas[64];
     for (int r = 0; r < n_rounds; r++) { ch_observe(ch, p_commits[r]); betas[r] = ch_sample(ch); }
     for (size_t j = 0; j < ((size_t)1 << log_f); j++) ch_observe(ch, p_final[j]);

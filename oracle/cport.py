@@ -44,6 +44,8 @@ def load():
                                           u64p, C.c_size_t]
         lib.lsp_oracle_gen_trace.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]
         lib.lsp_oracle_permutation_trace.argtypes = [u64p, C.c_size_t, C.c_uint32, u64p, u64p]
+        lib.lsp_oracle_set_field_consts.argtypes = [u64p, u64p]
+        lib.lsp_oracle_set_transcript_flags.argtypes = [C.c_int, C.c_int]
         lib.lsp_oracle_set_lookups.argtypes = [C.POINTER(C.c_uint32), C.c_int]
         _lib = lib
     return _lib
@@ -166,6 +168,16 @@ def permutation_trace(ab_limbs: np.ndarray, n: int, c: int, publics_limbs: np.nd
     if rc != 0:
         raise RuntimeError(f"lsp_oracle_permutation_trace failed: {rc} (b is not a permutation of a)")
     return tr
+
+
+def set_field_consts(generator: int, two_adic_root: int):
+    """Twin of `lsp_set_field_consts` (canonical ints in)."""
+    if load().lsp_oracle_set_field_consts(_p(_arr([generator])), _p(_arr([two_adic_root]))) != 0:
+        raise ValueError("bad field constants")
+
+
+def set_transcript_flags(alpha_before_openings: bool = True, observe_opened_values: bool = False):
+    load().lsp_oracle_set_transcript_flags(int(alpha_before_openings), int(observe_opened_values))
 
 
 def threads() -> int:

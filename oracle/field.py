@@ -56,10 +56,28 @@ def halve(a):
     return a * ((R_MOD + 1) // 2) % R_MOD
 
 
+class FieldConsts:
+    """The two parameters the fork-only `p3-bls12-377-fr` crate fixes and this tree cannot see:
+    `Val::GENERATOR` (the coset shift of the PCS) and `two_adic_generator(47)`.  Defaults: arkworks' FrConfig values.
+    Mirrors `lsp_set_field_consts`; tests switch them to show that nothing else in the prover depends on the defaults."""
+    generator = GENERATOR
+    two_adic_root = TWO_ADIC_ROOT
+
+
+def set_field_consts(generator: int = GENERATOR, two_adic_root: int = TWO_ADIC_ROOT):
+    assert generator % R_MOD != 0 and pow(generator, 1 << 31, R_MOD) != 1, "generator lies in a two-adic subgroup"
+    assert pow(two_adic_root, 1 << (TWO_ADICITY - 1), R_MOD) == R_MOD - 1, "not a primitive 2^47-th root of unity"
+    FieldConsts.generator, FieldConsts.two_adic_root = generator % R_MOD, two_adic_root % R_MOD
+
+
+def generator() -> int:
+    return FieldConsts.generator
+
+
 def two_adic_generator(bits: int) -> int:
-    """omega_{2^bits}: TWO_ADIC_ROOT squared (47 - bits) times."""
+    """omega_{2^bits}: the 2^47-th root squared (47 - bits) times."""
     assert 0 <= bits <= TWO_ADICITY
-    return pow(TWO_ADIC_ROOT, 1 << (TWO_ADICITY - bits), R_MOD)
+    return pow(FieldConsts.two_adic_root, 1 << (TWO_ADICITY - bits), R_MOD)
 
 
 def from_be_bytes_mod_order(b: bytes) -> int:

@@ -19,7 +19,7 @@ from dataclasses import dataclass
 from . import air as A
 from .challenger import HashChallenger
 from .dft import bit_reverse_rows, coset_lde_batch, idft
-from .field import (GENERATOR, R_MOD, batch_inverse, halve, inv, log2_ceil, log2_strict,
+from .field import (generator, R_MOD, batch_inverse, halve, inv, log2_ceil, log2_strict,
                     reverse_bits_len, two_adic_generator)
 from .merkle import MerkleTree, verify_batch
 from .poseidon2 import Poseidon2Params
@@ -55,7 +55,7 @@ class Domain:
         return x * self.gen() % R_MOD
 
     def create_disjoint_domain(self, min_size):
-        return Domain(log2_ceil(min_size), self.shift * GENERATOR % R_MOD)
+        return Domain(log2_ceil(min_size), self.shift * generator() % R_MOD)
 
     def split_domains(self, num_chunks):
         lc = log2_strict(num_chunks)
@@ -105,7 +105,7 @@ def pcs_commit(p: Poseidon2Params, fri: FriConfig, domains_and_mats):
     ldes = []
     for dom, mat in domains_and_mats:
         assert dom.size() == len(mat)
-        shift = GENERATOR * inv(dom.shift) % R_MOD
+        shift = generator() * inv(dom.shift) % R_MOD
         ldes.append(coset_lde_batch(mat, fri.log_blowup, shift))
     tree = MerkleTree(p, ldes)
     return tree.root, tree
@@ -226,13 +226,25 @@ def fri_prove(p, fri: FriConfig, fri_input, challenger, open_input, dbg=None):
                 pow_witness=pow_witness)
 
 
+class Transcript:
+    """Order of `TwoAdicFriPcs::open` / `verify` (SURVEY.md 8(c), A.9), mirrored by `lsp_set_transcript_flags`: the
+    pinned fork samples the batching challenge BEFORE the opened values are computed and never observes them (the
+    default); upstream Plonky3 after early 2025 observes the opened values and samples afterwards."""
+    alpha_before_openings = True
+    observe_opened_values = False
+
+
+def set_transcript_flags(alpha_before_openings: bool = True, observe_opened_values: bool = False):
+    Transcript.alpha_before_openings, Transcript.observe_opened_values = bool(alpha_before_openings), bool(observe_opened_values)
+
+
 def pcs_open(p, fri: FriConfig, rounds, challenger, dbg=None):
-    """rounds: list of (tree, points_per_matrix).  Fork-era order: alpha first."""
-    alpha = challenger.sample()
+    """rounds: list of (tree, points_per_matrix).  Transcript order: see `Transcript`."""
+    alpha = challenger.sample() if Transcript.alpha_before_openings else None
     max_h = max(t.height for t, _ in rounds)
     log_max_h = log2_strict(max_h)
     gen = two_adic_generator(log_max_h)
-    subgroup, x = [], GENERATOR
+    subgroup, x = [], generator()
     for _ in range(max_h):
         subgroup.append(x)
         x = x * gen % R_MOD
@@ -244,17 +256,28 @@ def pcs_open(p, fri: FriConfig, rounds, challenger, dbg=None):
             for z in pm:
                 if z not in inv_denoms:
                     inv_denoms[z] = batch_inverse([(x - z) % R_MOD for x in subgroup])
-    reduced = [0] * max_h
-    num_reduced = 0
+    # opened values first ("compute opened values with Lagrange interpolation", bench.log:34) ...
     opened = []
     for tree, pts in rounds:
         opened_round = []
         for mat, pm in zip(tree.mats, pts):
-            opened_mat = []
+            low = mat[:len(mat) >> fri.log_blowup]
+            opened_round.append([interpolate_coset(bit_reverse_rows(low), generator(), z) for z in pm])
+        opened.append(opened_round)
+    if Transcript.observe_opened_values:
+        for opened_round in opened:
+            for opened_mat in opened_round:
+                for ys in opened_mat:
+                    challenger.observe_slice(ys)
+    if alpha is None:
+        alpha = challenger.sample()
+    # ... then the reduced openings ("reduce rows", bench.log:35)
+    reduced = [0] * max_h
+    num_reduced = 0
+    for (tree, pts), opened_round in zip(rounds, opened):
+        for mat, pm, opened_mat in zip(tree.mats, pts, opened_round):
             w = len(mat[0])
-            for z in pm:
-                low = mat[:len(mat) >> fri.log_blowup]
-                ys = interpolate_coset(bit_reverse_rows(low), GENERATOR, z)
+            for z, ys in zip(pm, opened_mat):
                 apo = pow(alpha, num_reduced, R_MOD)
                 apow = [pow(alpha, i, R_MOD) for i in range(w)]
                 reduced_ys = sum(a * y for a, y in zip(apow, ys)) % R_MOD
@@ -263,9 +286,6 @@ def pcs_open(p, fri: FriConfig, rounds, challenger, dbg=None):
                     rr = sum(a * v for a, v in zip(apow, mat[r])) % R_MOD
                     reduced[r] = (reduced[r] + apo * ((rr - reduced_ys) % R_MOD) % R_MOD * idn[r]) % R_MOD
                 num_reduced += w
-                opened_mat.append(ys)
-            opened_round.append(opened_mat)
-        opened.append(opened_round)
     if dbg is not None:
         dbg["fri_alpha"] = alpha
         dbg["fri_input"] = list(reduced)
@@ -366,7 +386,14 @@ def verify(p: Poseidon2Params, fri: FriConfig, cfgs, proof, publics):
 
 
 def pcs_verify(p, fri: FriConfig, rounds, proof, challenger):
-    alpha = challenger.sample()
+    alpha = challenger.sample() if Transcript.alpha_before_openings else None
+    if Transcript.observe_opened_values:
+        for _, mats in rounds:
+            for _, pvs in mats:
+                for _, ys in pvs:
+                    challenger.observe_slice(ys)
+    if alpha is None:
+        alpha = challenger.sample()
     log_global_max = len(proof["commit_phase_commits"]) + fri.log_blowup + fri.log_final_poly_len
     betas = []
     for c in proof["commit_phase_commits"]:
@@ -396,7 +423,7 @@ def pcs_verify(p, fri: FriConfig, rounds, proof, challenger):
             for mat_opening, (dom, pvs) in zip(bo["opened_values"], mats):
                 log_h = dom.log_n + fri.log_blowup
                 rri = reverse_bits_len(index >> (log_global_max - log_h), log_h)
-                x = GENERATOR * pow(two_adic_generator(log_h), rri, R_MOD) % R_MOD
+                x = generator() * pow(two_adic_generator(log_h), rri, R_MOD) % R_MOD
                 ap, ro = ros.get(log_h, (1, 0))
                 for z, ps_at_z in pvs:
                     if len(ps_at_z) != len(mat_opening):

@@ -130,14 +130,18 @@ def row_major(cols):
 
 
 def build_trace(perm_inputs, alpha: int, delta: int, lookup_inputs=()):
-    """`RawTrace::push_traces` (`trace/src/lib.rs:62-92`): lookup traces first, then permutation traces;
-    pads every permutation input to the tallest, concatenates columns, shifts configs.  (Lookup inputs
-    must already have the common height: zero-padding a lookup changes its multiplicities.)"""
-    heights = [max(len(col) for col in a + b) for a, b in perm_inputs] + [len(l[0][0]) for l in lookup_inputs]
+    """`RawTrace::push_traces` (`trace/src/lib.rs:62-92`): the height is the tallest column of ANY input (:67-79);
+    lookup traces first, then permutation traces, each resized to that height with zero rows before its witness is
+    built (`push_lookup` :37-41 with `resize` `trace/src/lookup.rs:230-246`, filters included, so padded rows are
+    disabled; `push_permutation` :50-53 with `trace/src/permutation.rs:134-142`); columns concatenated, configs shifted."""
+    heights = [max(len(col) for col in a + b) for a, b in perm_inputs]
+    heights += [max([len(col) for col in l[0]] + [len(col) for t in l[1] for col in t]) for l in lookup_inputs]
     height = max(heights)
+    pad = lambda col: list(col) + [0] * (height - len(col))
     cols, cfgs = [], []
     for a, b, af, bf in lookup_inputs:
-        assert len(a[0]) == height
+        a, af = [pad(col) for col in a], pad(af)
+        b, bf = [[pad(col) for col in t] for t in b], [pad(f) for f in bf]
         cfg, lc = lookup_columns(a, b, af, bf, alpha, delta)
         cfg.shift(len(cols))
         cols += lc

@@ -35,6 +35,47 @@ def test_ragged_columns_are_zero_padded(pkg):
     assert np.array_equal(be, _be([a[0], a[1] + [0, 0]], [b[0] + [0, 0, 0], b[1] + [0]], 4))
 
 
+def test_decode_to_a_taller_common_height_pads_with_zero_rows(pkg):
+    """`push_traces` (trace/src/lib.rs:62-79) resizes every sub-trace to the tallest input before its witness is built:
+    `_decode` accepts rows >= the file's height, `_read_rows` allocates max(min_rows, height); a shorter target is an error."""
+    import ctypes as C
+    a, b = [[1, 2, 3], [4, 5]], [[3, 2, 1], [5, 4, 0]]
+    blob = OT.encode_raw_permutation_trace(a, b, "short")
+    be, rows, nc, _ = pkg.read_raw_permutation_trace(blob, _fill=0xEE, rows_target=8)
+    assert (rows, nc) == (8, 2)
+    assert np.array_equal(be, _be([a[0] + [0] * 5, a[1] + [0] * 6], [b[0] + [0] * 5, b[1] + [0] * 5], 8))
+    with pytest.raises(pkg.BackendError):
+        pkg.read_raw_permutation_trace(blob, rows_target=2)
+    lib = pkg.ffi.load()
+    r, n, ptr = C.c_size_t(), C.c_uint32(), C.c_void_p()
+    assert lib.lsp_cbor_permutation_read_rows(blob, len(blob), 8, C.byref(r), C.byref(n), None, 0, C.byref(ptr)) == 0
+    got = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(8 * 4 * 32,)).copy()
+    lib.lsp_host_free(ptr)
+    assert (r.value, n.value) == (8, 2) and np.array_equal(got, be)
+    # lookups: the filters of the padded rows are ZERO (resize, trace/src/lookup.rs:230-246), not the default one
+    lk = OT.synthetic_lookup_input(5, 2, 1, 4)
+    lblob = OT.encode_raw_lookup_trace(*lk, "lk")
+    lbe, lrows, na, nt, nb, _ = pkg.read_raw_lookup_trace(lblob, _fill=0xEE, rows_target=8)
+    plain, *_ = pkg.read_raw_lookup_trace(lblob)
+    stride = na + nt * nb + 1 + nt
+    assert lrows == 8 and np.array_equal(lbe[:4 * stride * 32], plain) and not lbe[4 * stride * 32:].any()
+
+
+def test_deeply_nested_unknown_value_is_rejected_not_a_stack_overflow(pkg):
+    """An unknown key whose value nests deeper than ciborium's recursion limit (256): a malformed file, not a crash."""
+    e = lambda x: int(x).to_bytes(32, "big")
+    good = cbor2.dumps({"a": [[e(1)]], "b": [[e(1)]], "name": "x"})
+    for opener, closer in ((b"\x81", b""), (b"\xc0", b""), (b"\x9f", b"\xff")):
+        for depth, ok in ((200, True), (100_000, False)):
+            junk = opener * depth + b"\x00" + closer * depth
+            blob = b"\xa4" + good[1:] + cbor2.dumps("zz") + junk
+            if ok:
+                assert pkg.read_raw_permutation_trace(blob)[1] == 1
+            else:
+                with pytest.raises(pkg.BackendError):
+                    pkg.read_raw_permutation_trace(blob)
+
+
 def test_byte_strings_indefinite_lengths_and_unknown_keys(pkg):
     e = lambda x: int(x).to_bytes(32, "big")
     plain = cbor2.dumps({"a": [[e(1), e(2)]], "b": [[e(2), e(1)]], "name": "x", "extra": [1, {"k": 2}]})

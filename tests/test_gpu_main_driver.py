@@ -56,6 +56,39 @@ def test_driver_proves_cbor_files_like_main(pkg, tmp_path):
     ctx.close()
 
 
+def test_driver_pads_inputs_of_different_heights_like_push_traces(pkg, tmp_path):
+    """`RawTrace::push_traces` (trace/src/lib.rs:62-92): the height is the tallest column of any input file and every
+    sub-trace is zero-padded to it before its witness is built -- a 16-row lookup beside a 64-row permutation proves."""
+    seed = 99
+    alpha, delta, consts = _draws(seed)
+    lk = OT.synthetic_lookup_input(7, 2, 1, 16, disabled_every=5)
+    pa, pb = OT.synthetic_permutation_input(8, 2, 64)
+    pa2, pb2 = OT.synthetic_permutation_input(9, 1, 32)
+    (tmp_path / "lookup_0.bin").write_bytes(OT.encode_raw_lookup_trace(*lk, "lookup_0"))
+    (tmp_path / "perm_0.bin").write_bytes(OT.encode_raw_permutation_trace(pa, pb, "perm_0"))
+    (tmp_path / "perm_1.bin").write_bytes(OT.encode_raw_permutation_trace(pa2, pb2, "perm_1"))
+    out = tmp_path / "proof.bin"
+    r = subprocess.run([str(EXE), "--lookup", str(tmp_path / "lookup_0.bin"), "--permutation", str(tmp_path / "perm_0.bin"),
+                        "--permutation", str(tmp_path / "perm_1.bin"), "--seed", str(seed), "--queries", "7", "--out", str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "proof accepted" in r.stdout and "64 rows" in r.stdout
+    words = np.frombuffer(out.read_bytes(), dtype=np.uint64)
+    p = Poseidon2Params(sbox_d=5, rounds_f=8, rounds_p=22, ext_initial=[consts[3 * i:3 * i + 3] for i in range(4)],
+                        ext_terminal=[consts[12 + 3 * i:15 + 3 * i] for i in range(4)], internal=consts[24:], internal_diag_m1=(1, 1, 2))
+    ctx = pkg.Context(0)
+    ctx.set_poseidon2(5, 8, 22, p.flat_constants(), p.internal_diag_m1)
+    cfgs, trace = OT.build_trace([(pa, pb), (pa2, pb2)], alpha, delta, [lk])
+    assert len(trace) == 64
+    from tests.test_gpu_lookup import _gpu_cfgs
+    fri = dict(log_blowup=3, log_final_poly_len=0, num_queries=7, proof_of_work_bits=0)
+    mine = pkg.prove(ctx, pkg.FriConfig(**fri), _gpu_cfgs(pkg, cfgs), trace, [alpha, delta])
+    assert np.array_equal(words, mine.words)
+    gd, _ = mine.to_dict()
+    OS.verify(p, OS.FriConfig(**fri), cfgs, gd, [alpha, delta])
+    ctx.close()
+
+
 def test_driver_fails_loudly_on_bad_input(tmp_path):
     (tmp_path / "junk.bin").write_bytes(b"\x00\x01\x02")
     r = subprocess.run([str(EXE), "--permutation", str(tmp_path / "junk.bin")], capture_output=True, text=True, timeout=120)

@@ -98,7 +98,7 @@ def test_random_shapes_against_the_c_port(pkg, gctx, p2params):
     from oracle import stark as OS
     cport.set_poseidon2(p2params)
     rng = np.random.default_rng(2026)
-    done = 0
+    done = refused = 0
     for trial in range(60):
         log_n = int(rng.integers(1, 13))
         c = int(rng.integers(1, 7))
@@ -112,16 +112,21 @@ def test_random_shapes_against_the_c_port(pkg, gctx, p2params):
         cfgs = [OA.AirPermutationConfig.standard(c)]
         g = [pkg.AirPermutationConfig(x.a_columns_ids, x.b_columns_ids, x.b_inverse_id, x.check_id) for x in cfgs]
         ofri = OS.FriConfig(**fri_kw)
+        if log_final == log_n:
+            # Zero commit-phase rounds (final polynomial as long as the trace): the reduced opening never enters the fold
+            # chain, so the low-degree test is vacuous -- the pinned verifier rejects every honest proof
+            # (FinalPolyMismatch) and would accept a forged all-zero final polynomial.  The library refuses the
+            # configuration on both sides instead of producing or checking such a proof.
+            with pytest.raises(pkg.BackendError, match="no commit-phase round"):
+                pkg.prove(gctx, pkg.FriConfig(**fri_kw), g, (tr, n, w), pkg.from_mont_array(pub))
+            refused += 1
+            continue
         cwords = cport.prove_limbs(ofri, tr, n, w, cfgs, pub)
         gproof = pkg.prove(gctx, pkg.FriConfig(**fri_kw), g, (tr, n, w), pkg.from_mont_array(pub))
         assert np.array_equal(cwords, gproof.words), (log_n, c, fri_kw)
-        # Zero commit-phase rounds (final polynomial as long as the trace): the prover side is well defined and must
-        # still match, but the restated verifiers -- like the pinned Plonky3 one they follow, whose query loop only adds
-        # the reduced opening inside a folding round -- reject such a proof (FinalPolyMismatch, code 5).  Keep that pinned.
-        want = 5 if log_final == log_n else 0
-        assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, gproof.words) == want, (log_n, c, fri_kw)
-        assert pkg.verify_code(gctx, pkg.FriConfig(**fri_kw), g, gproof, pkg.from_mont_array(pub)) == want, (log_n, c, fri_kw)
+        assert cport.verify_limbs(ofri, log_n, w, cfgs, pub, gproof.words) == 0, (log_n, c, fri_kw)
+        assert pkg.verify_code(gctx, pkg.FriConfig(**fri_kw), g, gproof, pkg.from_mont_array(pub)) == 0, (log_n, c, fri_kw)
         done += 1
         if done == 40:
             break
-    assert done >= 30
+    assert done >= 30 and refused >= 1

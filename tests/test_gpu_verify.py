@@ -173,16 +173,30 @@ def test_lookup_air_proofs(pkg, gctx, p2params, log_n, lookups, perms, fri_kw):
         assert want != 0 and pkg.verify_code(gctx, gfri, g, bad, [alpha, delta], log_n, w) == want
 
 
-def test_zero_round_proof_is_rejected_like_the_port(pkg, gctx, p2params):
-    """log_final_poly_len == log2(height): no commit-phase round, so the reduced opening never enters the fold
-    chain and the final-polynomial check fails -- in the pinned verifier, in the port and here."""
+def test_zero_round_fri_is_refused_by_prover_and_verifier(pkg, gctx, p2params):
+    """log_final_poly_len == log2(height): no commit-phase round, so the reduced opening never enters the fold chain and
+    the low-degree test would be vacuous (the pinned verifier rejects every honest such proof with FinalPolyMismatch --
+    oracle tests keep that pinned -- and a forged all-zero final polynomial would pass it).  The library refuses the
+    configuration on both sides with LSP_ERR_PARAM; so does a proof_of_work_bits above the 32 that sample_bits can test."""
     from oracle import cport
     cport.set_poseidon2(p2params)
-    fri_kw = dict(log_blowup=2, log_final_poly_len=3, num_queries=4, proof_of_work_bits=0)
-    cfgs, g, gproof, publics, pub = _perm_case(pkg, gctx, cport, 3, [1], fri_kw, 4242)
-    assert cport.verify_limbs(OS.FriConfig(**fri_kw), 3, gproof.width, cfgs, pub, gproof.words) == 5
-    with pytest.raises(pkg.VerificationError, match="FinalPolyMismatch"):
-        pkg.verify(gctx, pkg.FriConfig(**fri_kw), g, gproof, publics)
+    ok_kw = dict(log_blowup=2, log_final_poly_len=2, num_queries=4, proof_of_work_bits=0)
+    rng = F.SplitMix64(4242)
+    alpha, delta = rng.next_fr(), rng.next_fr()
+    cfgs, trace = OT.build_trace([OT.synthetic_permutation_input(4252, 1, 8)], alpha, delta, [])
+    g, publics, pub = _gpu_cfgs(pkg, cfgs), [alpha, delta], pkg.to_mont_array([alpha, delta])
+    gproof = pkg.prove(gctx, pkg.FriConfig(**ok_kw), g, trace, publics)
+    pkg.verify(gctx, pkg.FriConfig(**ok_kw), g, gproof, publics)
+    for bad_kw, msg in ((dict(ok_kw, log_final_poly_len=3), "no commit-phase round"), (dict(ok_kw, log_final_poly_len=4), "no commit-phase round"),
+                        (dict(ok_kw, proof_of_work_bits=33), "proof_of_work_bits")):
+        with pytest.raises(pkg.BackendError, match=msg):
+            pkg.prove(gctx, pkg.FriConfig(**bad_kw), g, trace, publics)
+        with pytest.raises(pkg.BackendError, match=msg):
+            pkg.verify_code(gctx, pkg.FriConfig(**bad_kw), g, gproof.words, publics, log_n=3, width=gproof.width)
+    # the CPU port's (release-build) behaviour that the refusal replaces stays pinned: its own zero-round proof fails at the final polynomial
+    zfri = OS.FriConfig(**dict(ok_kw, log_final_poly_len=3))
+    zwords = cport.prove(zfri, cfgs, trace, publics)
+    assert cport.verify_limbs(zfri, 3, gproof.width, cfgs, pub, zwords) == 5
 
 
 @pytest.mark.parametrize("d", [3, 7, 11, 17])
