@@ -176,6 +176,20 @@ int lsp_air_log_quotient_degree(int n_lookups, int n_perms);
 /* `fold_matrix(beta, m)`: in = vector of 2h elements viewed as h rows of 2; out h elements. */
 int lsp_fri_fold(lsp_ctx* ctx, const lsp_mat* in, const uint64_t beta[4], lsp_mat** out);
 
+/* `Pcs::open` of `TwoAdicFriPcs`, piece by piece, for a trait-level drop-in that keeps its own challenger
+ * (inside lsp_prove_* the same kernels run without leaving the device).
+ * lsp_eval_at: "compute opened values with Lagrange interpolation" (bench.log:34) -- the value at `z` of every column's
+ * interpolant, from the coefficient matrix lsp_coset_lde_batch returned (coefficients over the subgroup H_N: for a matrix
+ * committed on the domain s*H_N pass z/s).  values_out: width elements.
+ * lsp_reduce_openings: "reduce rows" (bench.log:35) -- the FRI input vector
+ *     sum over entries e of  alpha^(offset_e) * (sum_c alpha^c m_e[c](x) - sum_c alpha^c y_e[c]) / (x - z_e),   offset_{e+1} = offset_e + width_e
+ * over the L rows of the committed LDEs (x = GENERATOR * w_L^bitrev(row)); one entry per (matrix, point) in the order
+ * `open` walks them (trace at zeta, trace at zeta*g, then every quotient chunk at zeta). */
+int lsp_eval_at(lsp_ctx* ctx, const lsp_mat* coeffs, const uint64_t z[4], uint64_t* values_out);
+int lsp_reduce_openings(lsp_ctx* ctx, const lsp_mat* const* ldes, const uint64_t* points /* n_entries x 4 */,
+                        const uint64_t* const* opened /* per entry: width values */, int n_entries, const uint64_t alpha[4],
+                        lsp_mat** fri_input_out);
+
 /* ---- witness generation ---------------------------------------------------- */
 /* `RawPermutationTrace::get_trace` + `RawTrace::get_trace` (trace/src/permutation.rs:24-93,
  * trace/src/lib.rs:94-106): from the a/b input columns (host row-major rows x 2*n_cols, a

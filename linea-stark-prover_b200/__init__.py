@@ -7,5 +7,5 @@ it is imported under the module name `linea_stark_prover_b200` via
 """
 from . import ffi  # noqa: F401
 from .backend import (AirLookupConfig, AirPermutationConfig, BackendError, Comm, Context, FriConfig, GpuDft, GpuMmcs, Mat, Proof, Tree,  # noqa: F401
-                      fri_fold, from_mont_array, prove, prove_sharded, quotient_air, quotient_permutation, read_raw_lookup_trace, read_raw_permutation_trace, read_lookup_trace_once, read_permutation_trace_once,
+                      eval_at, reduce_openings, fri_fold, from_mont_array, prove, prove_sharded, quotient_air, quotient_permutation, read_raw_lookup_trace, read_raw_permutation_trace, read_lookup_trace_once, read_permutation_trace_once,
                       shard_plan, to_mont_array, VerificationError, verify, verify_code, VERIFY_REASONS)

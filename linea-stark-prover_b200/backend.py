@@ -656,6 +656,28 @@ def fri_fold(ctx: Context, vec: Mat, beta: int) -> Mat:
     return Mat(ctx, h)
 
 
+def eval_at(ctx: Context, coeffs: Mat, z: int) -> list:
+    """Opened values of every column at `z` from the coefficient matrix `coset_lde_batch(.., want_coeffs=True)` returned
+    ("compute opened values with Lagrange interpolation", bench.log:34): lsp_eval_at."""
+    out = np.empty((coeffs.width, 4), dtype=np.uint64)
+    ctx.check(ctx.lib.lsp_eval_at(ctx.h, coeffs.h, ffi.as_u64p(to_mont_array([z])), ffi.as_u64p(out)), "lsp_eval_at")
+    return from_mont_array(out)
+
+
+def reduce_openings(ctx: Context, entries, alpha: int) -> Mat:
+    """`Pcs::open`'s FRI input ("reduce rows", bench.log:35) from (lde Mat, point z, opened values ys) entries in `open`'s
+    order: lsp_reduce_openings."""
+    n = len(entries)
+    ldes = (C.c_void_p * n)(*[m.h for m, _, _ in entries])
+    pts = to_mont_array([z for _, z, _ in entries])
+    ys = [to_mont_array(y) for _, _, y in entries]
+    yptr = (ffi.u64p * n)(*[ffi.as_u64p(y) for y in ys])
+    h = C.c_void_p()
+    ctx.check(ctx.lib.lsp_reduce_openings(ctx.h, ldes, ffi.as_u64p(pts), yptr, n, ffi.as_u64p(to_mont_array([alpha])), C.byref(h)),
+              "lsp_reduce_openings")
+    return Mat(ctx, h)
+
+
 # ---------------------------------------------------------------------------
 # multi-GPU: one proof sharded over ranks (SURVEY.md 8(e))
 # ---------------------------------------------------------------------------

@@ -75,6 +75,8 @@ SIGNATURES = {
     "lsp_tree_free": (None, [vp, vp]),
     "lsp_quotient_permutation": (C.c_int, [vp, vp, C.c_int, C.c_int, C.POINTER(PermAirCfg), C.c_int, u64p, u64p,
                                            C.POINTER(vp)]),
+    "lsp_eval_at": (C.c_int, [vp, vp, u64p, u64p]),
+    "lsp_reduce_openings": (C.c_int, [vp, C.POINTER(vp), u64p, C.POINTER(u64p), C.c_int, u64p, C.POINTER(vp)]),
     "lsp_fri_fold": (C.c_int, [vp, vp, u64p, C.POINTER(vp)]),
     "lsp_proof_words": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(FriConfig)]),
     "lsp_prove_permutation": (C.c_int, [vp, C.POINTER(FriConfig), u64p, C.c_size_t, C.c_size_t,

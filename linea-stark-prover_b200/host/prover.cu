@@ -22,6 +22,8 @@
 //   1 pow witness
 //   per query: 1 index | W trace row, log2 L siblings | q chunk row, log2 L siblings |
 //              per round r: sibling value, (log2 L - 1 - r) siblings
+#include <algorithm>
+
 #include "../csrc/stark.cuh"
 #include "comm.hpp"
 #include "prove_kernels.cuh"
@@ -205,5 +207,89 @@ extern "C" int lsp_fri_fold(lsp_ctx* ctx, const lsp_mat* in, const uint64_t beta
         return rc;
     }
     *out = o;
+    return LSP_OK;
+}
+
+// ---------------------------------------------------------------------------
+// `Pcs::open` piece by piece, for a trait-level drop-in that keeps its own transcript:
+// opened values from the coefficients `lsp_coset_lde_batch` returned, and the reduced-opening vector FRI starts from.
+// ---------------------------------------------------------------------------
+extern "C" int lsp_eval_at(lsp_ctx* ctx, const lsp_mat* coeffs, const uint64_t z[4], uint64_t* values_out) {
+    if (!ctx || !coeffs || !z || !values_out || !is_pow2(coeffs->rows)) return LSP_ERR_PARAM;
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch S(ctx);
+    Fr *zd = nullptr, *y = nullptr;
+    LSP_TRY(S.get((void**)&zd, 32));
+    LSP_TRY(S.get((void**)&y, coeffs->width * 32));
+    LSP_CUDA(ctx, cudaMemcpyAsync(zd, z, 32, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // z[] is caller-owned
+    LSP_TRY(eval_columns_at(ctx, coeffs->d, coeffs->rows, coeffs->width, zd, y));
+    LSP_CUDA(ctx, cudaMemcpyAsync(values_out, y, coeffs->width * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return LSP_OK;
+}
+
+namespace {
+// s[0] = sum_c a^c ys[c]; pw[1] = pw[0] * a^w  (pw[0] = a^offset of this entry)
+__global__ void k_entry_scalars(const Fr* __restrict__ alpha, const Fr* __restrict__ ys, int w, Fr* __restrict__ s, Fr* __restrict__ pw) {
+    const Fr a = fr_load(alpha);
+    Fr acc = fr_load(ys + w - 1);
+    for (int i = w - 2; i >= 0; i--) acc = fr_add(fr_mul(acc, a), fr_load(ys + i));
+    fr_store(s, acc);
+    fr_store(pw + 1, fr_mul(fr_load(pw), fr_pow_u32(a, uint32_t(w))));
+}
+// out[p] (+)= a^offset * (sum_c a^c m[c][p] - sum_c a^c ys[c]) / (x_p - z)
+__global__ void __launch_bounds__(128) k_reduce_entry(const Fr* __restrict__ lde, size_t rows, int w, const Fr* __restrict__ alpha,
+                                                      const Fr* __restrict__ s, const Fr* __restrict__ pw, const Fr* __restrict__ inv_den,
+                                                      Fr* __restrict__ out, int accumulate) {
+    const Fr a = fr_load(alpha), rys = fr_load(s), off = fr_load(pw);
+    for (size_t p = blockIdx.x * size_t(blockDim.x) + threadIdx.x; p < rows; p += size_t(gridDim.x) * blockDim.x) {
+        Fr rr = fr_load_nc(lde + size_t(w - 1) * rows + p);
+        for (int c = w - 2; c >= 0; c--) rr = fr_add(fr_mul(rr, a), fr_load_nc(lde + size_t(c) * rows + p));
+        Fr v = fr_mul(fr_mul(off, fr_sub(rr, rys)), fr_load_nc(inv_den + p));
+        fr_store(out + p, accumulate ? fr_add(fr_load(out + p), v) : v);
+    }
+}
+}  // namespace
+
+extern "C" int lsp_reduce_openings(lsp_ctx* ctx, const lsp_mat* const* ldes, const uint64_t* points, const uint64_t* const* opened,
+                                   int n_entries, const uint64_t alpha[4], lsp_mat** fri_input_out) {
+    if (!ctx || !ldes || !points || !opened || n_entries <= 0 || !alpha || !fri_input_out) return LSP_ERR_PARAM;
+    const size_t L = ldes[0] ? ldes[0]->rows : 0;
+    if (!is_pow2(L) || L < 2) return set_err(ctx, LSP_ERR_PARAM, "LDE height must be a power of two >= 2");
+    size_t w_max = 0;
+    for (int e = 0; e < n_entries; e++) {
+        if (!ldes[e] || !opened[e] || ldes[e]->rows != L) return set_err(ctx, LSP_ERR_PARAM, "all committed matrices share one height on this path");
+        w_max = std::max(w_max, ldes[e]->width);
+    }
+    LSP_CUDA(ctx, cudaSetDevice(ctx->device));
+    Scratch S(ctx);
+    Fr *a = nullptr, *z = nullptr, *ys = nullptr, *s = nullptr, *pw = nullptr, *inv = nullptr;
+    LSP_TRY(S.get((void**)&a, 32));
+    LSP_TRY(S.get((void**)&z, size_t(n_entries) * 32));
+    LSP_TRY(S.get((void**)&ys, w_max * 32));
+    LSP_TRY(S.get((void**)&s, 32));
+    LSP_TRY(S.get((void**)&pw, size_t(n_entries + 1) * 32));
+    LSP_TRY(S.get((void**)&inv, L * 32));
+    LSP_CUDA(ctx, cudaMemcpyAsync(a, alpha, 32, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaMemcpyAsync(z, points, size_t(n_entries) * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const Fr one = host_pow2_inverse(0);
+    LSP_CUDA(ctx, cudaMemcpyAsync(pw, &one, 32, cudaMemcpyHostToDevice, ctx->stream));
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    lsp_mat* out = nullptr;
+    LSP_TRY(mat_alloc(ctx, L, 1, &out));
+    MatGuard guard{ctx, out};
+    for (int e = 0; e < n_entries; e++) {  // offset += width per (matrix, point), in the order given (A.9)
+        const int w = int(ldes[e]->width);
+        LSP_CUDA(ctx, cudaMemcpyAsync(ys, opened[e], size_t(w) * 32, cudaMemcpyHostToDevice, ctx->stream));
+        LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        LSP_LAUNCH(ctx, k_entry_scalars, 1, 1, 0, (const Fr*)a, (const Fr*)ys, w, s, pw + e);
+        Fr* invp[1] = {inv};
+        LSP_TRY(inverse_denominators(ctx, z + e, 1, ilog2(L), invp));
+        LSP_LAUNCH(ctx, k_reduce_entry, grid_for(ctx, L, 128), 128, 0, (const Fr*)ldes[e]->d, L, w, (const Fr*)a, (const Fr*)s, (const Fr*)(pw + e),
+                   (const Fr*)inv, out->d, e > 0 ? 1 : 0);
+    }
+    LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *fri_input_out = guard.release();
     return LSP_OK;
 }

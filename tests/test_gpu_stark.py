@@ -243,3 +243,36 @@ def test_prove_with_other_poseidon2_parameters(pkg, d, rf, rp, diag):
     states = [[rng.next_fr(), rng.next_fr(), 0] for _ in range(64)]
     assert [s[0] for s in ctx.permute(states)] == [OP.compress(p, s[0], s[1]) for s in states]
     ctx.close()
+
+
+@pytest.mark.parametrize("log_n,w,bits", [(3, 3, 2), (6, 5, 1), (8, 2, 3)])
+def test_pcs_open_pieces_eval_at_and_reduce_openings(pkg, gctx, p2params, log_n, w, bits):
+    """`Pcs::open` from its pieces (lsp_eval_at, lsp_reduce_openings) for a trait-level drop-in that keeps its own
+    challenger: opened values and the FRI input vector equal the oracle's `pcs_open` on a trace-like commit (two points) and
+    a quotient-like commit (two one-column matrices on the split, shifted domains)."""
+    from oracle.challenger import HashChallenger
+    rng = F.SplitMix64(1000 + log_n)
+    n = 1 << log_n
+    fri = OS.FriConfig(log_blowup=bits, log_final_poly_len=0, num_queries=2, proof_of_work_bits=0)
+    mat = [[rng.next_fr() for _ in range(w)] for _ in range(n)]
+    chunks = [[[rng.next_fr()] for _ in range(n)] for _ in range(2)]
+    dom = OS.Domain(log_n, 1)
+    qdoms = dom.create_disjoint_domain(2 * n).split_domains(2)
+    _, tree = OS.pcs_commit(p2params, fri, [(dom, mat)])
+    _, qtree = OS.pcs_commit(p2params, fri, list(zip(qdoms, chunks)))
+    z = rng.next_fr()
+    z2 = z * dom.gen() % F.R_MOD
+    ch = HashChallenger(p2params, [])
+    ch.observe(7)
+    dbg = {}
+    opened, _ = OS.pcs_open(p2params, fri, [(tree, [[z, z2]]), (qtree, [[z], [z]])], ch, dbg)
+    dft = pkg.GpuDft(gctx)
+    lde_t, co_t = dft.coset_lde_batch(gctx.upload(mat), bits, F.GENERATOR, want_coeffs=True)
+    assert pkg.eval_at(gctx, co_t, z) == opened[0][0][0] and pkg.eval_at(gctx, co_t, z2) == opened[0][0][1]
+    entries = [(lde_t, z, opened[0][0][0]), (lde_t, z2, opened[0][0][1])]
+    for c, qd in enumerate(qdoms):
+        lde_c, co_c = dft.coset_lde_batch(gctx.upload(chunks[c]), bits, F.GENERATOR * F.inv(qd.shift) % F.R_MOD, want_coeffs=True)
+        assert pkg.eval_at(gctx, co_c, z * F.inv(qd.shift) % F.R_MOD) == opened[1][c][0]
+        entries.append((lde_c, z, opened[1][c][0]))
+    got = pkg.reduce_openings(gctx, entries, dbg["fri_alpha"]).rows()
+    assert [r[0] for r in got] == dbg["fri_input"]
