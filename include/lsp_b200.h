@@ -318,6 +318,21 @@ int lsp_verify_permutation(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t log
 int lsp_merkle_verify_batch(lsp_ctx* ctx, const uint64_t root[4], uint32_t log_height, size_t index,
                             const uint64_t* row, size_t row_len, const uint64_t* siblings);
 
+/* ---- proof serialisation (host only) ------------------------------------------------------------------- */
+/* The flat array of lsp_prove_* <-> a byte stream in the field order of `p3_uni_stark::Proof` as bincode (fixed-width
+ * little-endian integers, a u64 length before every Vec) writes the derived `Serialize`, every field element as its
+ * canonical integer in 32 little-endian bytes (ark-serialize's CanonicalSerialize), behind a 32-byte header
+ * ("LSPP", version, FriConfig, width, log_q).  The reference never serialises a proof and the fork's serde impl is not
+ * available: this is this library's documented format (host/serialize.cu), not a claim about the fork's bytes.
+ * `_deserialize` with proof_out == NULL only reports the shape; non-canonical elements, wrong lengths and trailing bytes
+ * are LSP_ERR_PARAM.  The per-query indices are not part of `Proof`: the rebuilt flat array carries a marker in those
+ * slots and lsp_verify_air substitutes the indices it samples. */
+size_t lsp_proof_serialized_bytes(uint32_t log_n, uint32_t width, uint32_t log_q, const lsp_fri_config* fri);
+int lsp_proof_serialize(const uint64_t* proof, size_t proof_words, uint32_t log_n, uint32_t width, uint32_t log_q,
+                        const lsp_fri_config* fri, uint8_t* out, size_t out_cap, size_t* out_len);
+int lsp_proof_deserialize(const uint8_t* bytes, size_t len, uint32_t* log_n_out, uint32_t* width_out, uint32_t* log_q_out,
+                          lsp_fri_config* fri_out, uint64_t* proof_out, size_t proof_words_cap, size_t* proof_words_out);
+
 /* ---- multi-GPU: one proof sharded by row ranges of the LDE ---------- */
 typedef struct lsp_comm lsp_comm;
 /* NCCL bootstrap: rank 0 calls lsp_nccl_unique_id, ships the 128 bytes to the other ranks

@@ -481,6 +481,32 @@ class Proof:
     def __init__(self, words: np.ndarray, log_n: int, width: int, log_q: int, fri: FriConfig):
         self.words, self.log_n, self.width, self.log_q, self.fri = words, log_n, width, log_q, fri
 
+    def serialize(self) -> bytes:
+        """`Proof` as bytes (lsp_proof_serialize: bincode-style field order, canonical little-endian elements)."""
+        lib, cf = ffi.load(), self.fri.c_struct()
+        cap = int(lib.lsp_proof_serialized_bytes(self.log_n, self.width, self.log_q, C.byref(cf)))
+        buf, n = C.create_string_buffer(cap), C.c_size_t()
+        rc = lib.lsp_proof_serialize(ffi.as_u64p(np.ascontiguousarray(self.words)), self.words.size, self.log_n, self.width, self.log_q,
+                                     C.byref(cf), buf, cap, C.byref(n))
+        if rc != 0 or n.value != cap:
+            raise BackendError(f"lsp_proof_serialize failed ({rc})")
+        return buf.raw
+
+    @staticmethod
+    def deserialize(blob: bytes) -> "Proof":
+        """The inverse (lsp_proof_deserialize).  The per-query index slots hold the "not carried" marker: the device
+        verifier fills in what it samples.  Raises `BackendError` on a malformed stream."""
+        lib = ffi.load()
+        log_n, width, log_q, cf, words = C.c_uint32(), C.c_uint32(), C.c_uint32(), ffi.FriConfig(), C.c_size_t()
+        if lib.lsp_proof_deserialize(blob, len(blob), C.byref(log_n), C.byref(width), C.byref(log_q), C.byref(cf), None, 0, C.byref(words)) != 0:
+            raise BackendError("malformed serialised proof")
+        out = np.empty(words.value, dtype=np.uint64)
+        if lib.lsp_proof_deserialize(blob, len(blob), C.byref(log_n), C.byref(width), C.byref(log_q), C.byref(cf), ffi.as_u64p(out),
+                                     out.size, C.byref(words)) != 0:
+            raise BackendError("malformed serialised proof")
+        fri = FriConfig(cf.log_blowup, cf.log_final_poly_len, cf.num_queries, cf.proof_of_work_bits)
+        return Proof(out, log_n.value, width.value, log_q.value, fri)
+
     def to_dict(self):
         """Same shape as the reference's `Proof` struct, canonical ints."""
         w, q = self.width, 1 << self.log_q

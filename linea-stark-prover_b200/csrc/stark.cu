@@ -10,6 +10,10 @@
 
 using namespace lsp;
 
+#ifndef LSP_GRIND_MINB
+#define LSP_GRIND_MINB 8   // resident 128-thread blocks per SM, as for the other one-thread-per-permutation kernels
+#endif
+
 namespace lsp {
 
 // ===========================================================================
@@ -86,29 +90,45 @@ __global__ void __launch_bounds__(32) k_ch_sample_bits(const __grid_constant__ P
     }
 }
 
-// grind: each thread tests witnesses base + tid + k*stride against a clone of the
-// challenger; the smallest passing witness of the first chunk that has one wins,
-// which makes the result deterministic (the reference's rayon find_any is not).
+// grind: every trial hashes [input_buffer..., witness] (a clone of the challenger observing the witness, then
+// sample_bits).  All trials share every sponge block but the last, so one warp absorbs those once (k_ch_grind_prefix) and
+// a trial is ONE permutation; each thread tests the witness base + its global index, and the smallest passing witness
+// of the first chunk that has one wins, which makes the result deterministic (the reference's rayon find_any is not).
+struct GrindPrefix {
+    Fr s[3];     // sponge state after the blocks that do not hold the witness
+    Fr last;     // input[n-1]: shares the witness' block when n is odd
+    int n_odd;
+};
 template <int D>
-__global__ void __launch_bounds__(128, 4) k_ch_grind_chunk(const __grid_constant__ P2Params P, const DevChallenger* ch, int bits,
-                                                           unsigned long long base, unsigned long long* best) {
+__global__ void __launch_bounds__(32) k_ch_grind_prefix(const __grid_constant__ P2Params P, const DevChallenger* ch, GrindPrefix* out) {
+    const int lane = threadIdx.x & 31, k = lane / 3, w = lane - 3 * k;
+    const int n = ch->n_input, full = n & ~1;   // the witness is element n: blocks (0,1) .. (full-2, full-1) come first
+    Fr s = fr_zero();
+#pragma unroll 1
+    for (int i = 0; i < full; i += 2) {
+        if (w < 2) s = ch->input[i + w];
+        p2_permute_tri<D>(P, s, w, 3 * k);
+    }
+    if (lane < 3) out->s[lane] = s;
+    if (lane == 0) {
+        out->n_odd = n & 1;
+        out->last = (n & 1) ? ch->input[n - 1] : fr_zero();
+    }
+}
+template <int D>
+__global__ void __launch_bounds__(128, LSP_GRIND_MINB) k_ch_grind_chunk(const __grid_constant__ P2Params P, const GrindPrefix* __restrict__ pre, int bits,
+                                                                        unsigned long long base, unsigned long long* best) {
     unsigned long long w = base + blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     // witness as a field element: canonical w -> Montgomery
     Fr wf = fr_zero();
     wf.l[0] = uint32_t(w);
     wf.l[1] = uint32_t(w >> 32);
     wf = fr_mul(wf, fr_const(FR_R2));
-    // hash_iter([input_buffer..., witness]): odd count -> the last block is [input[n-1], witness];
-    // even count -> [witness] alone with state[1] stale
+    // the witness' block: [input[n-1], witness] when the buffer held an odd count, else [witness] alone with the
+    // second word stale (overwrite-mode sponge)
     LSP_P2_SLOT_DECL(128);
-    Fr s0 = fr_zero(), s1 = fr_zero(), s2 = fr_zero();
-    const int n = ch->n_input;
-#pragma unroll 1
-    for (int i = 0; i <= n; i += 2) {
-        s0 = i < n ? ch->input[i] : wf;
-        if (i + 1 <= n) s1 = i + 1 < n ? ch->input[i + 1] : wf;
-        p2_permute<D, 128>(P, s0, s1, s2, LSP_P2_SLOT(128));
-    }
+    Fr s0 = pre->n_odd ? pre->last : wf, s1 = pre->n_odd ? wf : pre->s[1], s2 = pre->s[2];
+    p2_permute<D, 128>(P, s0, s1, s2, LSP_P2_SLOT(128));
     Fr c = fr_from_mont(s0);
     uint32_t low = bits >= 32 ? c.l[0] : (c.l[0] & ((1u << bits) - 1u));
     if (low == 0) atomicMin(best, w);
@@ -206,13 +226,16 @@ int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out)
     if (bits == 0) {
         LSP_CUDA(ctx, cudaMemsetAsync(best, 0, 8, ctx->stream));  // witness 0 always passes
     } else {
-        // expected 2^bits trials; test chunks until one contains a witness (host reads one u64 per chunk)
-        const unsigned long long chunk = 1ull << 22;
+        // expected 2^bits trials; test chunks until one contains a witness (the host reads one u64 per chunk)
+        GrindPrefix* pre = nullptr;
+        LSP_TRY(tmp.get((void**)&pre, sizeof(GrindPrefix)));
+        LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_grind_prefix<D>, 1, 32, 0, ctx->p2, (const DevChallenger*)ch, pre));
+        const unsigned long long chunk = bits < 24 ? (1ull << 22) : (1ull << 25);
         unsigned long long h_best = ~0ull;
         for (unsigned long long base = 0;; base += chunk) {
             LSP_CUDA(ctx, cudaMemsetAsync(best, 0xff, 8, ctx->stream));
             LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_grind_chunk<D>, unsigned(chunk / 128), 128, 0, ctx->p2,
-                                                         (const DevChallenger*)ch, bits, base, best));
+                                                         (const GrindPrefix*)pre, bits, base, best));
             LSP_CUDA(ctx, cudaMemcpyAsync(&h_best, best, 8, cudaMemcpyDeviceToHost, ctx->stream));
             LSP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             if (h_best != ~0ull) break;

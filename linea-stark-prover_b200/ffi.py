@@ -83,6 +83,11 @@ SIGNATURES = {
                                         C.POINTER(PermAirCfg), C.c_int, u64p, u64p, C.c_size_t, f32p]),
     "lsp_prove_permutation_dev": (C.c_int, [vp, C.POINTER(FriConfig), vp, C.POINTER(PermAirCfg), C.c_int, u64p,
                                             u64p, C.c_size_t, f32p]),
+    "lsp_proof_serialized_bytes": (C.c_size_t, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(FriConfig)]),
+    "lsp_proof_serialize": (C.c_int, [u64p, C.c_size_t, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(FriConfig), C.c_char_p, C.c_size_t,
+                                      C.POINTER(C.c_size_t)]),
+    "lsp_proof_deserialize": (C.c_int, [C.c_char_p, C.c_size_t, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                        C.POINTER(FriConfig), u64p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "lsp_nccl_unique_id": (C.c_int, [C.POINTER(C.c_uint8)]),
     "lsp_comm_init_nccl": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_uint8), C.POINTER(vp)]),
     "lsp_comm_init_local": (C.c_int, [vp, C.c_int, C.POINTER(vp)]),

@@ -147,7 +147,7 @@ void on_all_ranks(std::vector<Rank>& ranks, F body) {
 
 int main(int argc, char** argv) {
     std::vector<std::string> lookups, perms;
-    std::string out_path;
+    std::string out_path, out_ser_path;
     uint64_t seed = 0xB200;
     int device = 0, sbox_d = 5, repeat = 1, gpus = 1;
     lsp_fri_config fri = {3, 0, 33, 0};  // bin/src/main.rs:58-64
@@ -170,6 +170,7 @@ int main(int argc, char** argv) {
         else if (a == "--device") device = atoi(need("--device"));
         else if (a == "--gpus") gpus = atoi(need("--gpus"));
         else if (a == "--out") out_path = need("--out");
+        else if (a == "--out-serialized") out_ser_path = need("--out-serialized");
         else if (a == "--repeat") repeat = atoi(need("--repeat"));
         else {
             fprintf(stderr, "unknown argument %s\n", a.c_str());
@@ -401,6 +402,14 @@ int main(int argc, char** argv) {
             std::ofstream f(out_path, std::ios::binary);
             f.write(reinterpret_cast<const char*>(proof.data()), std::streamsize(words * 8));
             printf("proof written to %s (layout in DESIGN.md section 7)\n", out_path.c_str());
+        }
+        if (!out_ser_path.empty()) {  // `Proof` in struct order (lsp_proof_serialize): what a verifier elsewhere would receive
+            std::vector<uint8_t> bytes(lsp_proof_serialized_bytes(uint32_t(log_n), col, uint32_t(log_q), &fri));
+            size_t n_bytes = 0;
+            CHECK(ctx, lsp_proof_serialize(proof.data(), words, uint32_t(log_n), col, uint32_t(log_q), &fri, bytes.data(), bytes.size(), &n_bytes));
+            std::ofstream f(out_ser_path, std::ios::binary);
+            f.write(reinterpret_cast<const char*>(bytes.data()), std::streamsize(n_bytes));
+            printf("serialised proof (%zu bytes) written to %s\n", n_bytes, out_ser_path.c_str());
         }
         return 0;
     };

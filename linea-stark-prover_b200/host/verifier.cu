@@ -85,6 +85,23 @@ __global__ void __launch_bounds__(128) k_verify_canonical(const Fr* __restrict__
     }
 }
 
+// A proof rebuilt from its serialised form (lsp_proof_deserialize) does not carry the per-query indices -- `Proof` has no
+// such field, the verifier samples them: those slots hold the all-ones marker and receive the sampled index here.
+__global__ void k_adopt_sampled_indices(Fr* __restrict__ queries, size_t per_query, const uint32_t* __restrict__ idx, int n_queries) {
+    const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (qi >= n_queries) return;
+    Fr* slot = queries + size_t(qi) * per_query;
+    const Fr v = fr_load(slot);
+    bool marker = true;
+#pragma unroll
+    for (int i = 0; i < 8; i++) marker = marker && v.l[i] == 0xffffffffu;
+    if (marker) {
+        Fr r = fr_zero();
+        r.l[0] = idx[qi];
+        fr_store(slot, r);
+    }
+}
+
 struct VerifyArgs {
     const Fr *proof, *p_local, *p_next, *p_chunks, *p_commits, *p_final, *p_queries;
     const Fr *publics, *scal, *betas;
@@ -387,8 +404,9 @@ extern "C" int lsp_verify_air(lsp_ctx* ctx, const lsp_fri_config* fri, uint32_t 
     T.pow_low = reinterpret_cast<uint32_t*>(status);
     T.idx = idx;
     LSP_CUDA(ctx, cudaMemsetAsync(status + 2, 0, 4, ctx->stream));
-    LSP_LAUNCH(ctx, k_verify_canonical, grid_for(ctx, proof_elems, 128), 128, 0, (const Fr*)proof, proof_elems, status + 2);
     LSP_TRY(verify_transcript(ctx, ch, T));
+    LSP_LAUNCH(ctx, k_adopt_sampled_indices, unsigned((nq + 63) / 64), 64, 0, const_cast<Fr*>(A.p_queries), A.per_query, (const uint32_t*)idx, nq);
+    LSP_LAUNCH(ctx, k_verify_canonical, grid_for(ctx, proof_elems, 128), 128, 0, (const Fr*)proof, proof_elems, status + 2);
     LSP_LAUNCH(ctx, k_verify_fold_ood, unsigned((nq + VERIFY_BLOCK - 1) / VERIFY_BLOCK + 1), VERIFY_BLOCK, 0, A);
     LSP_LAUNCH(ctx, k_verify_path_jobs, unsigned((n_jobs + 127) / 128), 128, 0, A, jobs);
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_merkle_paths_tri<D>, unsigned((n_jobs + 9) / 10), 32, 0, ctx->p2, (const PathJob*)jobs, n_jobs));

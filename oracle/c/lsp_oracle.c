@@ -385,11 +385,19 @@ typedef struct { fr in[CH_CAP]; int n; } chal_t;
 static void ch_observe(chal_t* c, fr x) { if (c->n < CH_CAP) c->in[c->n++] = x; }
 static fr ch_sample(chal_t* c) { fr o = hash_slice(c->in, (size_t)c->n); c->in[0] = o; c->n = 1; return o; }
 static uint64_t ch_sample_bits(chal_t* c, int bits) { fr v = fr_canonical(ch_sample(c)); return bits >= 64 ? v.l[0] : (v.l[0] & ((1ull << bits) - 1)); }
+/* smallest witness (deterministic; the reference's rayon `find_any` is not): chunks of candidates tested in parallel */
 static fr ch_grind(chal_t* c, int bits) {
-    for (uint64_t w = 0;; w++) {
-        chal_t t; t.n = c->n; memcpy(t.in, c->in, (size_t)c->n * sizeof(fr));
-        ch_observe(&t, fr_from_u64(w));
-        if (ch_sample_bits(&t, bits) == 0) { fr wf = fr_from_u64(w); ch_observe(c, wf); (void)ch_sample_bits(c, bits); return wf; }
+    const uint64_t chunk = 4096;
+    for (uint64_t base = 0;; base += chunk) {
+        uint64_t best = UINT64_MAX;
+        #pragma omp parallel for schedule(static) reduction(min : best)
+        for (uint64_t w = base; w < base + chunk; w++) {
+            if (w > best) continue;
+            chal_t t; t.n = c->n; memcpy(t.in, c->in, (size_t)c->n * sizeof(fr));
+            ch_observe(&t, fr_from_u64(w));
+            if (ch_sample_bits(&t, bits) == 0 && w < best) best = w;
+        }
+        if (best != UINT64_MAX) { fr wf = fr_from_u64(best); ch_observe(c, wf); (void)ch_sample_bits(c, bits); return wf; }
     }
 }
 

@@ -35,6 +35,14 @@ def test_ragged_columns_are_zero_padded(pkg):
     assert np.array_equal(be, _be([a[0], a[1] + [0, 0]], [b[0] + [0, 0, 0], b[1] + [0]], 4))
 
 
+def test_fast_numpy_encoder_is_the_oracle_encoder(pkg):
+    """The vectorised encoder the full-size tests use writes the same bytes as the oracle's cbor2 encoder."""
+    from tests.proofs import fast_cbor_permutation_trace
+    for n, c, seed in ((1, 1, 1), (23, 2, 2), (24, 3, 3), (300, 1, 4), (70000, 1, 5)):
+        a, b = OT.synthetic_permutation_input(seed, c, n) if n < 1000 else ([[(i * 2654435761) % F.R_MOD for i in range(n)]], [[i for i in range(n)]])
+        assert fast_cbor_permutation_trace(_be(a, b, n), n, c, "nm") == OT.encode_raw_permutation_trace(a, b, "nm")
+
+
 def test_decode_to_a_taller_common_height_pads_with_zero_rows(pkg):
     """`push_traces` (trace/src/lib.rs:62-79) resizes every sub-trace to the tallest input before its witness is built:
     `_decode` accepts rows >= the file's height, `_read_rows` allocates max(min_rows, height); a shorter target is an error."""

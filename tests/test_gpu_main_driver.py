@@ -34,9 +34,9 @@ def test_driver_proves_cbor_files_like_main(pkg, tmp_path):
     pa, pb = OT.synthetic_permutation_input(2, 3, n)
     (tmp_path / "lookup_0.bin").write_bytes(OT.encode_raw_lookup_trace(*lk, "lookup_0"))
     (tmp_path / "perm_0.bin").write_bytes(OT.encode_raw_permutation_trace(pa, pb, "perm_0"))
-    out = tmp_path / "proof.bin"
+    out, ser = tmp_path / "proof.bin", tmp_path / "proof.lspp"
     r = subprocess.run([str(EXE), "--lookup", str(tmp_path / "lookup_0.bin"), "--permutation", str(tmp_path / "perm_0.bin"), "--seed",
-                        str(seed), "--queries", "9", "--out", str(out)], capture_output=True, text=True, timeout=300)
+                        str(seed), "--queries", "9", "--out", str(out), "--out-serialized", str(ser)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "Proving..." in r.stdout and "commit to trace data" in r.stdout
     assert "Verifying..." in r.stdout and "proof accepted" in r.stdout          # main.rs:88-96
@@ -53,6 +53,11 @@ def test_driver_proves_cbor_files_like_main(pkg, tmp_path):
     assert np.array_equal(words, mine.words)
     gd, _ = mine.to_dict()
     OS.verify(p, OS.FriConfig(**fri), cfgs, gd, [alpha, delta])
+    # the serialised form the driver wrote is the mirror's, and what it carries verifies on the device and in the oracle
+    assert ser.read_bytes() == mine.serialize()
+    back = pkg.Proof.deserialize(ser.read_bytes())
+    pkg.verify(ctx, pkg.FriConfig(**fri), _gpu_cfgs(pkg, cfgs), back, [alpha, delta])
+    assert back.to_dict()[0] == gd
     ctx.close()
 
 

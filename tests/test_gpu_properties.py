@@ -130,3 +130,25 @@ def test_random_shapes_against_the_c_port(pkg, gctx, p2params):
         if done == 40:
             break
     assert done >= 30 and refused >= 1
+
+
+@pytest.mark.parametrize("bits", [16, 20])
+def test_grinding_at_real_bit_counts_finds_the_cpu_ports_witness(pkg, gctx, p2params, bits):
+    """`proof_of_work_bits` at sizes where grinding is real work (the reference's commented setting is 29,
+    bin/src/main.rs:62; timed by tools/grind_bench.py): the device grinder -- one permutation per trial on top of the
+    shared sponge prefix -- must find the SMALLEST witness, i.e. the one the CPU port's ordered search finds, for an odd
+    and an even number of buffered observations (final polynomial of 2 resp. 1 coefficients ahead of the witness)."""
+    from oracle import cport
+    from oracle import stark as OS
+    cport.set_poseidon2(p2params)
+    cport.set_threads(0)
+    for log_blowup, log_final in ((1, 0), (1, 1), (2, 0)):
+        fri_kw = dict(log_blowup=log_blowup, log_final_poly_len=log_final, num_queries=3, proof_of_work_bits=bits)
+        pub, tr, n, w = cport.gen_trace(77 + bits + log_final, 1, 3)
+        cfgs = [OA.AirPermutationConfig.standard(1)]
+        g = [pkg.AirPermutationConfig(x.a_columns_ids, x.b_columns_ids, x.b_inverse_id, x.check_id) for x in cfgs]
+        gproof = pkg.prove(gctx, pkg.FriConfig(**fri_kw), g, (tr, n, w), pkg.from_mont_array(pub))
+        assert np.array_equal(cport.prove_limbs(OS.FriConfig(**fri_kw), tr, n, w, cfgs, pub), gproof.words), fri_kw
+        assert pkg.verify_code(gctx, pkg.FriConfig(**fri_kw), g, gproof, pkg.from_mont_array(pub)) == 0
+        d, _ = gproof.to_dict()
+        assert d["opening_proof"]["pow_witness"] > 0

@@ -184,15 +184,17 @@ def test_full_size_prove_verifies_and_matches_cpu_port(pkg):
     ctx.close()
 
 
-@pytest.mark.parametrize("name,log_n,c,log_blowup", [
-    ("cfg3: 3x3 columns, 2^22 rows, blowup 8", 22, 3, 3),
-    ("cfg4a: 3x32 columns, 2^20 rows, blowup 2", 20, 32, 1),
-    ("cfg4b: 3x32 columns, 2^20 rows, blowup 4", 20, 32, 2),
+@pytest.mark.parametrize("name,log_n,c,log_blowup,port_seconds", [
+    ("cfg3: 3x3 columns, 2^22 rows, blowup 8", 22, 3, 3, 210),
+    ("cfg4a: 3x32 columns, 2^20 rows, blowup 2", 20, 32, 1, 55),
+    ("cfg4b: 3x32 columns, 2^20 rows, blowup 4", 20, 32, 2, 110),
 ])
-def test_baseline_configs_verify(pkg, name, log_n, c, log_blowup):
-    """BASELINE.json configs[2] and configs[3] as parity cases: the trace comes from the CPU port's
-    generator (trace/src/permutation.rs semantics), the device witness generator must reproduce it,
-    and the GPU proof must be accepted by the (restated) verifier; a flipped bit must be rejected."""
+def test_baseline_configs_bit_exact(pkg, name, log_n, c, log_blowup, port_seconds):
+    """BASELINE.json configs[2] and configs[3] as parity cases: the trace comes from the CPU port's generator
+    (trace/src/permutation.rs semantics), the device witness generator must reproduce it, the GPU proof must be accepted
+    by both verifiers (a flipped bit rejected for the same reason) -- and it must BE the CPU port's proof, word for word.
+    The port needs 1-4 minutes of host time at these sizes: cfg4a always runs in full; the word-for-word leg of cfg3 and
+    cfg4b runs under LSP_FULL_PARITY=1 (recorded per round in profiles/), their acceptance legs always."""
     import os
     import numpy as np
     from oracle import cport
@@ -201,6 +203,7 @@ def test_baseline_configs_verify(pkg, name, log_n, c, log_blowup):
         pytest.skip("LSP_SKIP_BIG set")
     p = Poseidon2Params.from_seed(0xB200, sbox_d=5)
     cport.set_poseidon2(p)
+    cport.set_threads(0)
     ctx = pkg.Context(0)
     ctx.set_poseidon2(p.sbox_d, p.rounds_f, p.rounds_p, p.flat_constants(), p.internal_diag_m1)
     pub, tr, n, w = cport.gen_trace(0xC0FFEE + log_n, c, log_n)
@@ -219,6 +222,57 @@ def test_baseline_configs_verify(pkg, name, log_n, c, log_blowup):
     why = cport.verify_limbs(ofri, log_n, w, cfgs, pub, bad)
     assert why != 0
     assert pkg.verify_code(ctx, pkg.FriConfig(**fri_kw), _gpu_cfgs(pkg, cfgs), bad, pkg.from_mont_array(pub), log_n, w) == why
+    # a second rank layout of the same proof: sharded over the ranks the blowup allows, on this one device
+    comm = pkg.Comm.local(ctx, 2)
+    assert np.array_equal(pkg.prove_sharded(comm, pkg.FriConfig(**fri_kw), _gpu_cfgs(pkg, cfgs), dev, pkg.from_mont_array(pub)).words, gproof.words)
+    comm.close()
+    if port_seconds <= 60 or os.environ.get("LSP_FULL_PARITY"):
+        assert np.array_equal(cport.prove_limbs(ofri, tr, n, w, cfgs, pub), gproof.words), name
+    ctx.close()
+
+
+def test_cfg5_standin_cbor_file_through_lsp_prove_is_bit_exact(pkg, tmp_path):
+    """BASELINE configs[4] (the stripped zkevm.bin): its stand-in is a 6+6-column `RawPermutationTrace` CBOR file of 2^19
+    rows (the `mxp` shape of bench.log:2-13, ~390 MB).  The C++ `main` (lsp_prove: file -> device witness -> prove ->
+    device verify) must write the proof the Python mirror produces from the same bytes, and that proof must be the CPU
+    port's, word for word, on the 14-column trace."""
+    import os
+    import subprocess
+    import numpy as np
+    from oracle import cport
+    from oracle.poseidon2 import Poseidon2Params
+    from tests.proofs import fast_cbor_permutation_trace
+    from tests.test_gpu_main_driver import EXE, _draws
+    if os.environ.get("LSP_SKIP_BIG"):
+        pytest.skip("LSP_SKIP_BIG set")
+    log_n, c, seed = int(os.environ.get("LSP_CFG5_LOG_N", "19")), 6, 20260
+    n = 1 << log_n
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, size=(n, c, 32), dtype=np.uint8)
+    a[:, :, 0] &= 0x0F                                           # below 2^252 < r: canonical values
+    be = np.ascontiguousarray(np.concatenate([a, a[rng.permutation(n)]], axis=1)).reshape(-1)
+    path = tmp_path / "mxp.bin"
+    path.write_bytes(fast_cbor_permutation_trace(be, n, c, "mxp"))
+    out = tmp_path / "proof.bin"
+    r = subprocess.run([str(EXE), "--permutation", str(path), "--seed", str(seed), "--out", str(out)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "proof accepted" in r.stdout and f"{n} rows x 14 columns" in r.stdout
+    words = np.frombuffer(out.read_bytes(), dtype=np.uint64)
+    path.unlink()
+    alpha, delta, consts = _draws(seed)
+    p = Poseidon2Params(sbox_d=5, rounds_f=8, rounds_p=22, ext_initial=[consts[3 * i:3 * i + 3] for i in range(4)],
+                        ext_terminal=[consts[12 + 3 * i:15 + 3 * i] for i in range(4)], internal=consts[24:], internal_diag_m1=(1, 1, 2))
+    ctx = pkg.Context(0)
+    ctx.set_poseidon2(5, 8, 22, p.flat_constants(), p.internal_diag_m1)
+    pub = pkg.to_mont_array([alpha, delta])
+    trace = ctx.permutation_trace_be(be, n, c, pub)
+    cfgs = [OA.AirPermutationConfig.standard(c)]
+    mine = pkg.prove(ctx, pkg.FriConfig(), _gpu_cfgs(pkg, cfgs), trace, [alpha, delta])
+    assert np.array_equal(words, mine.words)
+    cport.set_poseidon2(p)
+    cport.set_threads(0)
+    tr = trace.download_array()
+    assert np.array_equal(cport.prove_limbs(OS.FriConfig(), tr, n, 14, cfgs, pub), mine.words)
     ctx.close()
 
 
