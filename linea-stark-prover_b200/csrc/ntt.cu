@@ -278,6 +278,49 @@ int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width
     return LSP_OK;
 }
 
+// ---- a FRACTION of a coset (sharding over more ranks than there are cosets) -------------------------
+// Rows [sub*M, (sub+1)*M), M = N >> log_s, of destination block `block`: in bit-reversed order they are the points
+// p(S_c * w_N^(k0 + 2^log_s * m)), m < M, with k0 = bitrev_{log_s}(sub) -- the coset sigma * H_M, sigma = S_c * w_N^k0.
+// On it x^M = sigma^M =: u is constant, so p folds to degree < M:
+//     p(x) = sum_{i0 < M} x^i0 * sum_{t < 2^log_s} a[i0 + M t] u^t
+// (the "DIF pre-pass of log2(G/B) stages"), and the rest is the ordinary coset evaluation of the folded polynomial with
+// shift sigma.  `next` != 0 evaluates p(w_N * x) instead: the NEXT trace row of every point (the quotient's second operand).
+__global__ void k_subblock_consts(const FieldConsts* __restrict__ fc, const Fr* __restrict__ shift, int log_n, int added_bits, int block,
+                                  int log_s, int sub, int next, Fr* __restrict__ out /* [sigma, u] */) {
+    const uint32_t coset = bitrev32(uint32_t(block), added_bits), k0 = bitrev32(uint32_t(sub), log_s) + (next ? 1u : 0u);
+    Fr sigma = fr_mul(fr_load(shift), fr_pow_u32(fr_two_adic_generator(fc, log_n + added_bits), coset));
+    sigma = fr_mul(sigma, fr_pow_u32(fr_two_adic_generator(fc, log_n), k0));
+    Fr u = sigma;
+    for (int i = 0; i < log_n - log_s; i++) u = fr_sqr(u);
+    fr_store(out, sigma);
+    fr_store(out + 1, u);
+}
+__global__ void __launch_bounds__(128) k_fold_coeffs(const Fr* __restrict__ coeffs, size_t n, size_t m, int s, const Fr* __restrict__ u_dev,
+                                                     Fr* __restrict__ out, size_t width) {
+    const Fr u = fr_load(u_dev);
+    const size_t total = m * width;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t c = i / m, i0 = i - c * m;
+        const Fr* a = coeffs + c * n + i0;
+        Fr acc = fr_load_nc(a + size_t(s - 1) * m);
+        for (int t = s - 2; t >= 0; t--) acc = fr_add(fr_mul(acc, u), fr_load_nc(a + size_t(t) * m));
+        fr_store(out + i, acc);
+    }
+}
+int coset_evaluate_subblock(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift, int block, int log_s,
+                            int sub, bool next, Fr* out, size_t out_col_stride) {
+    const int log_n = ilog2(n);
+    if (log_s < 0 || log_s > log_n) return set_err(ctx, LSP_ERR_PARAM, "a coset of 2^%d rows cannot be split 2^%d ways", log_n, log_s);
+    const size_t m = n >> log_s;
+    Fr *sc = nullptr, *folded = nullptr;
+    Scratch tmp(ctx);
+    LSP_TRY(tmp.get((void**)&sc, 64));
+    LSP_TRY(tmp.get((void**)&folded, m * width * 32));
+    LSP_LAUNCH(ctx, k_subblock_consts, 1, 1, 0, (const FieldConsts*)ctx->fc, shift, log_n, added_bits, block, log_s, sub, next ? 1 : 0, sc);
+    LSP_LAUNCH(ctx, k_fold_coeffs, grid_for(ctx, m * width, 128), 128, 0, coeffs, n, m, 1 << log_s, (const Fr*)(sc + 1), folded, width);
+    return coset_evaluate_blocks(ctx, folded, m, width, 0, sc, 0, 1, out, out_col_stride);
+}
+
 // out (L x W, column-major, bit-reversed row order) from coefficients (N x W).
 int coset_evaluate(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift, Fr* out) {
     return coset_evaluate_blocks(ctx, coeffs, n, width, added_bits, shift, 0, 1 << added_bits, out, n << added_bits);

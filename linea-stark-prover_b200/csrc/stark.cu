@@ -230,7 +230,8 @@ int challenger_grind(lsp_ctx* ctx, DevChallenger* ch, int bits, Fr* witness_out)
         GrindPrefix* pre = nullptr;
         LSP_TRY(tmp.get((void**)&pre, sizeof(GrindPrefix)));
         LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_grind_prefix<D>, 1, 32, 0, ctx->p2, (const DevChallenger*)ch, pre));
-        const unsigned long long chunk = bits < 24 ? (1ull << 22) : (1ull << 25);
+        // ~2 expected witnesses per chunk (a chunk without one: e^-2), between one wave of the device and 2^25
+        const unsigned long long chunk = 1ull << (bits + 1 < 17 ? 17 : (bits + 1 > 25 ? 25 : bits + 1));
         unsigned long long h_best = ~0ull;
         for (unsigned long long base = 0;; base += chunk) {
             LSP_CUDA(ctx, cudaMemsetAsync(best, 0xff, 8, ctx->stream));
@@ -445,6 +446,7 @@ int inverse_denominators(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m,
 // ===========================================================================
 struct QuotientArgs {
     const Fr* lde;        // column-major, column stride = lde_rows
+    const Fr* lde_next;   // optional: p(w_N x) on the same rows (same shape); nullptr = next rows are in `lde`
     size_t lde_rows;
     int log_n, log_q;
     PermCfgDev cfg;
@@ -494,8 +496,9 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
         const size_t pg = A.p0 + pi;                 // global storage row
         const uint32_t i = bitrev32(uint32_t(pg), lnq);
         const uint32_t i_next = (i + q) & uint32_t(nq - 1);
-        const size_t p = pg - A.p_base;              // local row (next row lies in the same N-row block)
-        const size_t pn = size_t(bitrev32(i_next, lnq)) - A.p_base;
+        const long long p = (long long)(pg - A.p_base);   // local row
+        const long long pn = A.lde_next ? p + (long long)(A.lde_next - A.lde)          // second matrix, same row
+                                        : (long long)(size_t(bitrev32(i_next, lnq)) - A.p_base);   // same N-row block
         const uint32_t c = i & (q - 1);
         // x = g * w_{Nq}^i
         Fr wi = (i < nq / 2) ? fr_load_nc(A.tw_nq + i) : fr_neg(fr_load_nc(A.tw_nq + (i - nq / 2)));
@@ -516,12 +519,13 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
 // whole chunks).  `lde` points at storage row p_base of every column (column stride lde_rows);
 // chunk c = bitrev(block) is written to chunks + c*N.
 int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, size_t p_base, int log_n, int log_q, const PermCfgDev& cfg,
-                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks) {
+                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks, const Fr* lde_next) {
     int lnq = log_n + log_q;
     size_t nq = size_t(1) << lnq;
     if (lnq < 1) return set_err(ctx, LSP_ERR_PARAM, "trace of height 1 with a single quotient chunk is unsupported");
-    if (p0 + count > nq || (count & ((size_t(1) << log_n) - 1)) || (p0 & ((size_t(1) << log_n) - 1)))
-        return set_err(ctx, LSP_ERR_PARAM, "quotient range must cover whole chunks");
+    const size_t whole = (size_t(1) << log_n) - 1;
+    if (p0 + count > nq || (!lde_next && ((count | p0) & whole)))
+        return set_err(ctx, LSP_ERR_PARAM, "quotient range must cover whole chunks unless the next rows are supplied");
     // The selector tables -- Z_H per chunk, 1/(x - 1) and 1/(x - w_N^-1) over the quotient domain -- depend on the
     // shape only, not on the trace or the challenges: built once per (log_n, log_q, row range) and kept with the
     // context (2 * count * 32 bytes), like the twiddles.  Saves two inverse-denominator sweeps and a Fermat
@@ -547,6 +551,7 @@ int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, siz
     LSP_TRY(twiddles(ctx, lnq, false, &tw));
     QuotientArgs A;
     A.lde = lde;
+    A.lde_next = lde_next;
     A.lde_rows = lde_rows;
     A.log_n = log_n;
     A.log_q = log_q;

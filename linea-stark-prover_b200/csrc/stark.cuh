@@ -58,6 +58,9 @@ int interpolate_columns(lsp_ctx* ctx, const Fr* in, size_t n, size_t width, Fr* 
 int coset_evaluate(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift_dev, Fr* out);
 int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift_dev, int block0,
                           int n_blocks, Fr* out, size_t out_col_stride);
+// rows [sub*M, (sub+1)*M), M = n >> log_s, of row block `block` only (a rank that owns a fraction of a coset); `next`: of p(w_N x)
+int coset_evaluate_subblock(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift_dev, int block, int log_s,
+                            int sub, bool next, Fr* out, size_t out_col_stride);
 
 // ---- core.cu ---------------------------------------------------------------
 // device row-major (host layout) -> device column-major
@@ -112,9 +115,10 @@ struct PermCfgDev {  // flattened LineaAIR config list in device memory: lookups
 // LineaAIR::eval folded by powers of the STARK challenge (ProverConstraintFolder / VerifierConstraintFolder,
 // acc = acc * alpha + constraint): lookups first, then permutations, as `oracle/air.py` orders them.
 // Row `p` is the local row, `pn` the next one; element (column c, row r) is lde[c * lde_rows + r].  The quotient
-// kernel calls it on LDE rows, the verifier on the opened values (lde_rows = 1, p = 0, pn = width).
-__device__ __forceinline__ Fr fold_air_constraints(const PermCfgDev& cfg, const Fr* __restrict__ lde, size_t lde_rows, size_t p,
-                                                   size_t pn, const Fr& alpha_air, const Fr& delta, const Fr& alpha,
+// kernel calls it on LDE rows, the verifier on the opened values (lde_rows = 1, p = 0, pn = width).  `pn` is a signed
+// element offset: a caller whose next rows live in a second matrix of the same shape passes pn = row + (next - lde).
+__device__ __forceinline__ Fr fold_air_constraints(const PermCfgDev& cfg, const Fr* __restrict__ lde, size_t lde_rows, long long p,
+                                                   long long pn, const Fr& alpha_air, const Fr& delta, const Fr& alpha,
                                                    const Fr& is_first, const Fr& is_last, const Fr& is_trans) {
     const Fr one = fr_one();
     Fr acc = fr_zero();
@@ -228,8 +232,11 @@ int inverse_denominators_range(lsp_ctx* ctx, const Fr* z_dev, int n_points, int 
 int quotient_permutation(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, int log_n, int log_q, const PermCfgDev& cfg,
                          const Fr* publics_dev, const Fr* alpha_dev, Fr* chunks /* q columns of N */);
 
+// storage rows [p0, p0 + count) of the quotient domain; `lde` points at storage row p_base.  lde_next == nullptr: the next row
+// of every row lies in the same matrix (whole cosets); else it is read from lde_next at the SAME local row (a rank that
+// owns a fraction of a coset evaluates p(w_N x) on its own points, coset_evaluate_subblock(next)).
 int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, size_t p_base, int log_n, int log_q, const PermCfgDev& cfg,
-                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks);
+                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks, const Fr* lde_next = nullptr);
 
 // y[c] = sum_k coeffs[c][k] * z^k
 int eval_columns_at(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, const Fr* z_dev, Fr* y_dev);

@@ -39,7 +39,7 @@ def main():
         pkg.verify(ctx, fri, cfgs, proof, publics)
         d, _ = proof.to_dict()
         wit = int(d["opening_proof"]["pow_witness"])
-        chunk = 1 << 22 if bits < 24 else 1 << 25
+        chunk = 1 << min(25, max(17, bits + 1))
         trials = ((wit // chunk) + 1) * chunk if bits else 0
         grind_ms = tm["grind_query"]
         rows.append(dict(bits=bits, prove_s=round(wall, 4), grind_query_ms=round(grind_ms, 3), witness=wit, trials_tested=trials,
