@@ -181,8 +181,8 @@ int main(int argc, char** argv) {
         fprintf(stderr, "usage: lsp_prove [--lookup f.cbor]... [--permutation f.cbor]... [--seed S] [--gpus N] [--out proof.bin]\n");
         return 2;
     }
-    if (gpus < 1 || (gpus & (gpus - 1)) || (1u << fri.log_blowup) < unsigned(gpus)) {
-        fprintf(stderr, "--gpus must be a power of two no larger than the blowup (2^%u)\n", fri.log_blowup);
+    if (gpus < 1 || (gpus & (gpus - 1)) || gpus > 8) {  // more ranks than cosets is fine: a rank then owns a fraction of one
+        fprintf(stderr, "--gpus must be a power of two, at most 8 (one node)\n");
         return 2;
     }
 

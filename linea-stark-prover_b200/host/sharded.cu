@@ -293,7 +293,7 @@ struct RankState {
     Fr* sc = nullptr;
     DevChallenger* ch = nullptr;
     Fr* proof = nullptr;
-    Fr *lde_t = nullptr, *dig_t = nullptr, *top_t = nullptr;
+    Fr *lde_t = nullptr, *lde_next = nullptr, *dig_t = nullptr, *top_t = nullptr;
     const Fr** cols_t = nullptr;
     Fr *chunks = nullptr, *coef_q = nullptr, *lde_q = nullptr, *dig_q = nullptr, *top_q = nullptr;
     const Fr** cols_q = nullptr;
@@ -373,13 +373,21 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     const int log_n = ilog2(n), log_q = lsp_air_log_quotient_degree_cfg(lookups, n_lookups, cfgs, n_cfgs), q = 1 << log_q;
     const int log_b = int(fri->log_blowup), log_l = log_n + log_b;
     LSP_TRY(check_fri_config(ctx, fri, log_n, log_q));
-    if (log_g > log_b) return set_err(ctx, LSP_ERR_PARAM, "%d ranks need at least %d cosets (log_blowup >= %d)", G, G, log_g);
+    // More ranks than cosets: a rank owns a FRACTION 2^-log_s of one coset (row block of N); its rows are the sub-coset
+    // the first log_s DIF stages would hand it (coset_evaluate_subblock).  8 rows is the alignment of the 1/(x - z) tables.
+    const int log_s = log_g > log_b ? log_g - log_b : 0;
+    if (log_s > 0 && (log_n - log_s) < 3) return set_err(ctx, LSP_ERR_PARAM, "%d ranks are too many for 2^%d x 2^%d rows", G, log_n, log_b);
     const size_t need = lsp_proof_words(log_n, uint32_t(W), log_q, fri);
     if (proof_words < need) return set_err(ctx, LSP_ERR_PARAM, "proof buffer too small: %zu < %zu words", proof_words, need);
     LSP_CUDA(ctx, cudaSetDevice(ctx->device));
 
     const size_t L = size_t(1) << log_l, Lr = L >> log_g;
-    const int Bs = (1 << log_b) >> log_g;  // cosets (row blocks of N) per rank
+    const int Bs = (1 << log_b) >> log_g;  // whole cosets (row blocks of N) per rank; 0 when a rank owns a fraction of one
+    // this rank's rows of a committed matrix, from its coefficients: whole cosets, or the sub-coset of one
+    auto lde_local = [&](const Fr* coeffs, size_t width, const Fr* shift_dev, int rank, bool next, Fr* out) -> int {
+        if (log_s == 0) return coset_evaluate_blocks(ctx, coeffs, n, width, log_b, shift_dev, rank * Bs, Bs, out, Lr);
+        return coset_evaluate_subblock(ctx, coeffs, n, width, log_b, shift_dev, rank >> log_s, log_s, rank & ((1 << log_s) - 1), next, out, Lr);
+    };
     const int n_rounds = log_n - int(fri->log_final_poly_len);
     const int log_f = log_b + int(fri->log_final_poly_len);
     const size_t proof_elems = need / 4;
@@ -451,7 +459,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_TRY(P.get(&R.top_t, 2 * size_t(G) * 32));
         LSP_TRY(P.get(&R.cols_t, W * sizeof(Fr*)));
         // ---- commit to trace data: this rank's cosets only ------------------------------------------
-        LSP_TRY(coset_evaluate_blocks(ctx, coef_t, n, W, log_b, R.sc + S_GEN, R.rank * Bs, Bs, R.lde_t, Lr));
+        LSP_TRY(lde_local(coef_t, W, R.sc + S_GEN, R.rank, false, R.lde_t));
     }
     mark();  // 1
     auto commit_sharded = [&](auto lde_of, auto cols_of, auto dig_of, auto top_of, int width_cols, size_t proof_slot) -> int {
@@ -487,12 +495,37 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_TRY(P.get(&R.chunks, size_t(q) * n * 32));
         // row block b of the quotient domain (b < q) holds chunk bitrev(b); its owner computes it (the blocks of one
         // rank are adjacent: one launch)
-        const int b0 = R.rank * Bs, b1 = std::min(q, b0 + Bs);
-        if (b0 < b1)
-            LSP_TRY(quotient_permutation_range(ctx, R.lde_t, Lr, size_t(b0) * n, log_n, log_q, cfg_dev, R.sc + S_PUB0, R.sc + S_ALPHA,
-                                               size_t(b0) * n, size_t(b1 - b0) * n, R.chunks));
+        if (log_s == 0) {
+            const int b0 = R.rank * Bs, b1 = std::min(q, b0 + Bs);
+            if (b0 < b1)
+                LSP_TRY(quotient_permutation_range(ctx, R.lde_t, Lr, size_t(b0) * n, log_n, log_q, cfg_dev, R.sc + S_PUB0, R.sc + S_ALPHA,
+                                                   size_t(b0) * n, size_t(b1 - b0) * n, R.chunks));
+        } else {
+            // A fraction of a coset: the next row of a row is NOT among this rank's rows (adjacent trace rows are far
+            // apart in bit-reversed order).  The rank evaluates p(w_N x) on its own points instead -- one more local LDE
+            // for the ranks inside the quotient domain -- and every rank's scattered share of a chunk is summed below.
+            LSP_CUDA(ctx, cudaMemsetAsync(R.chunks, 0, size_t(q) * n * 32, ctx->stream));
+            if ((R.rank >> log_s) < q) {
+                LSP_TRY(P.get(&R.lde_next, Lr * W * 32));
+                LSP_TRY(lde_local(coef_t, W, R.sc + S_GEN, R.rank, true, R.lde_next));
+                LSP_TRY(quotient_permutation_range(ctx, R.lde_t, Lr, size_t(R.rank) * Lr, log_n, log_q, cfg_dev, R.sc + S_PUB0, R.sc + S_ALPHA,
+                                                   size_t(R.rank) * Lr, Lr, R.chunks, R.lde_next));
+            }
+        }
     }
-    for (int b = 0; b < q && G > 1; b++) {  // the one bulk exchange: N field elements per chunk
+    if (log_s > 0) {  // disjoint shares + zeros: an integer sum assembles every chunk on every rank
+        std::vector<void*> buf(H);
+        for (size_t i = 0; i < H; i++) buf[i] = st[i].chunks;
+        if (cm->local) {
+            Fr* summed = nullptr;
+            LSP_TRY(P.get(&summed, size_t(q) * n * 32));
+            LSP_TRY(coll_allreduce_sum(cm, ranks, buf, size_t(q) * n * 32, summed));
+            for (size_t i = 0; i < H; i++) st[i].chunks = summed;
+        } else {
+            LSP_TRY(coll_allreduce_sum(cm, ranks, buf, size_t(q) * n * 32, nullptr));
+        }
+    }
+    for (int b = 0; b < q && G > 1 && log_s == 0; b++) {  // the one bulk exchange: N field elements per chunk
         const int c = int(bitrev_host(uint32_t(b), log_q));
         const int owner = b / Bs;
         std::vector<void*> buf(H);
@@ -514,8 +547,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_LAUNCH(ctx, k_chunk_consts, 1, 32, 0, (const FieldConsts*)ctx->fc, (const Fr*)nullptr, log_n, log_q, R.sc + S_CHUNK_SHIFT, (Fr*)nullptr, (Fr*)nullptr);
         LSP_TRY(interpolate_columns(ctx, R.chunks, n, q, R.coef_q));
         for (int c = 0; c < q; c++)
-            LSP_TRY(coset_evaluate_blocks(ctx, R.coef_q + size_t(c) * n, n, 1, log_b, R.sc + S_CHUNK_SHIFT + c, R.rank * Bs, Bs,
-                                          R.lde_q + size_t(c) * Lr, Lr));
+            LSP_TRY(lde_local(R.coef_q + size_t(c) * n, 1, R.sc + S_CHUNK_SHIFT + c, R.rank, false, R.lde_q + size_t(c) * Lr));
     }
     LSP_TRY(commit_sharded([](RankState& R) { return R.lde_q; }, [](RankState& R) { return R.cols_q; }, [](RankState& R) { return R.dig_q; },
                            [](RankState& R) { return R.top_q; }, q, 1));

@@ -169,7 +169,8 @@ def test_main_flow_cbor_files_to_proof(pkg, gctx, p2params):
 
 
 @pytest.mark.parametrize("log_n,lookups,perms,world,blowup", [(4, [(1, 1, 0)], [], 2, 2), (5, [(2, 2, 5)], [2], 4, 3), (6, [(1, 2, 0)], [1], 8, 3),
-                                                              (10, [(2, 1, 7)], [3], 2, 3)])
+                                                              (10, [(2, 1, 7)], [3], 2, 3),
+                                                              (6, [(1, 1, 0)], [1], 8, 2), (7, [(2, 2, 3)], [], 16, 2)])   # more ranks than cosets
 def test_sharded_prove_of_lookup_air_equals_single_gpu(pkg, gctx, p2params, log_n, lookups, perms, world, blowup):
     """The sharded prove with 4 quotient chunks (chunk owners spread over the ranks) on the local communicator."""
     import numpy as np

@@ -27,7 +27,11 @@ def _gpu_cfgs(pkg, cfgs):
 
 
 @pytest.mark.parametrize("log_n,c,world,blowup", [(4, 2, 1, 3), (4, 2, 2, 3), (5, 3, 4, 3), (6, 1, 8, 3), (5, 2, 2, 1),
-                                                  (10, 3, 2, 3), (11, 2, 4, 3), (12, 1, 8, 3)])
+                                                  (10, 3, 2, 3), (11, 2, 4, 3), (12, 1, 8, 3),
+                                                  # more ranks than cosets (BASELINE configs[3]: blowup 2 and 4 on 8 GPUs): a rank owns a
+                                                  # fraction of a coset, evaluates the NEXT rows itself, chunks assembled by a sum
+                                                  (4, 2, 4, 1), (5, 1, 8, 1), (6, 3, 8, 2), (6, 2, 4, 1), (10, 3, 8, 1), (12, 2, 8, 2),
+                                                  (13, 1, 16, 1)])
 def test_sharded_prove_equals_single_gpu(pkg, gctx, p2params, log_n, c, world, blowup):
     cfgs, trace, publics = _instance(log_n, c, 100 + log_n + world)
     fri = pkg.FriConfig(log_blowup=blowup, num_queries=17)
@@ -46,10 +50,11 @@ def test_sharded_prove_equals_single_gpu(pkg, gctx, p2params, log_n, c, world, b
 
 
 def test_sharded_rejects_too_many_ranks(pkg, gctx):
-    cfgs, trace, publics = _instance(4, 1, 5)
-    comm = pkg.Comm.local(gctx, 4)
-    with pytest.raises(pkg.BackendError):
-        pkg.prove_sharded(comm, pkg.FriConfig(log_blowup=1), _gpu_cfgs(pkg, cfgs), trace, publics)  # 4 ranks, 2 cosets
+    """A rank may own a fraction of a coset, but not fewer than 8 rows of it (the alignment of the 1/(x - z) tables)."""
+    cfgs, trace, publics = _instance(3, 1, 5)
+    comm = pkg.Comm.local(gctx, 8)
+    with pytest.raises(pkg.BackendError, match="too many"):
+        pkg.prove_sharded(comm, pkg.FriConfig(log_blowup=1), _gpu_cfgs(pkg, cfgs), trace, publics)  # 8 ranks, 2 cosets of 8 rows
     comm.close()
 
 
