@@ -42,6 +42,7 @@ struct lsp_ctx {
     size_t pinned_bytes = 0;
     // optional per-kernel timing (bench.py / profiles): CUDA events around every launch
     unsigned* grid_barrier = nullptr;   // arrival counter of the fused tree-top kernel
+    bool ntt_smem_opt_in = false;       // k_ntt_tile's > 48 KiB of dynamic shared memory enabled on this device
     // shape-only selector tables of the quotient kernel, keyed by (log_n, log_q, first row, rows)
     struct QuotSel {
         lsp::Fr *scal = nullptr, *inv0 = nullptr, *inv1 = nullptr;

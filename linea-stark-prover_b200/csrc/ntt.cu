@@ -13,7 +13,8 @@
 //              bit-reversed row order of the LDE falls out of DIF for free:
 //              coset c lands in row block bitrev(c), position bitrev(k).
 // A pass runs up to LSP_NTT_MAX_T butterfly stages on a tile of 2^t elements held
-// in shared memory as two 16-byte planes (conflict-free 128-bit accesses).
+// in shared memory as two 16-byte planes (conflict-free 128-bit accesses), two stages per barrier in registers, with
+// the tile's twiddles and coset factors staged in shared memory once and reused by every column (k_ntt_tile).
 #include "stark.cuh"
 
 using namespace lsp;
@@ -65,6 +66,9 @@ struct NttPass {
     int pow_lo_bits;
     int scale_store;    // multiply by `scale` on store (1/N)
     Fr scale;
+    int width;          // columns of this launch (k_ntt_tile loops over them)
+    int cols_per_block;
+    int n_z;            // cosets of this launch
 };
 
 __device__ __forceinline__ void smem_put(uint4* plo, uint4* phi, int i, const Fr& v) {
@@ -79,71 +83,121 @@ __device__ __forceinline__ Fr smem_get(const uint4* plo, const uint4* phi, int i
     return r;
 }
 
-// One block = one tile of 2^t elements of one column (of one coset); blockDim.x = max(2^(t-1), 32).
+// ---- the pass kernel the LDE runs on: register-blocked, column-looped --------------------------------------------
+// One block = one tile of 2^t elements (one coset), LOOPED over up to `cols_per_block` columns:
+//   * the twiddles the tile's t stages need (2^t - 1 of them: stage with local bit lb uses 2^lb) are fetched ONCE into
+//     shared memory and reused by every column, instead of one global load per butterfly;
+//   * the coset power S_c^g of every element (two table entries multiplied) is computed ONCE per tile and kept in shared
+//     memory: one product per element per column instead of two;
+//   * a thread owns FOUR elements and runs TWO butterfly stages on them in registers between barriers (a radix-4 step
+//     costs 4 products and 3 twiddle reads; in a prime field there is no cheaper radix-4 butterfly): half the barriers
+//     and half the shared-memory traffic of one stage per barrier, and two independent products in flight per thread.
+// Shared memory: tile + twiddles (+ factors) = 2 or 3 planes of 2^t x 32 bytes (96 KiB at t = 10 with factors).
+constexpr int NTT_TILE_MINB = 2;   // resident blocks per SM the kernel is compiled for (<= 128 registers at 256 threads)
+
 template <bool DIF>
-__global__ void __launch_bounds__(512) k_ntt_pass(const __grid_constant__ NttPass P) {
-    extern __shared__ uint4 smem[];
-    const int t = P.t;
-    const int tile = 1 << t;
-    uint4* plo = smem;
-    uint4* phi = smem + tile;
-    const size_t lo_mask = (size_t(1) << P.bit_lo) - 1;
-    const size_t tile_id = blockIdx.x;
-    const size_t idx_lo = tile_id & lo_mask;
-    const size_t idx_hi = tile_id >> P.bit_lo;
-    const size_t base = (idx_hi << (P.bit_lo + t)) | idx_lo;  // + j << bit_lo
-    const int z = blockIdx.z;
-    const Fr* src = P.src + blockIdx.y * P.src_col_stride + z * P.src_z_stride;
-    Fr* dst = P.dst + blockIdx.y * P.dst_col_stride + z * P.dst_z_stride;
-
-    for (int j = threadIdx.x; j < tile; j += blockDim.x) {
-        size_t g = base + (size_t(j) << P.bit_lo);
-        size_t sidx = P.bitrev_load ? size_t(bitrev32(uint32_t(g), P.log_n)) : g;
-        Fr v = fr_load_nc(src + sidx);
-        if (P.pow_lo) {
-            size_t n_lo = size_t(1) << P.pow_lo_bits, n_hi = size_t(1) << (P.log_n - P.pow_lo_bits);
-            Fr a = fr_load_nc(P.pow_lo + z * n_lo + (g & (n_lo - 1)));
-            Fr b = fr_load_nc(P.pow_hi + z * n_hi + (g >> P.pow_lo_bits));
-            v = fr_mul(v, fr_mul(a, b));
-        }
-        smem_put(plo, phi, j, v);
+__device__ __forceinline__ void ntt_bfly(Fr& u, Fr& v, const Fr& w, bool trivial) {
+    if (DIF) {
+        const Fr d = fr_sub(u, v);
+        u = fr_add(u, v);
+        v = trivial ? d : fr_mul(d, w);
+    } else {
+        const Fr vw = trivial ? v : fr_mul(v, w);
+        v = fr_sub(u, vw);
+        u = fr_add(u, vw);
     }
-    __syncthreads();
+}
 
-    const int nbf = tile >> 1;
-    for (int s = 0; s < t; s++) {
-        // DIF walks the local bits from high to low, DIT from low to high
-        const int lb = DIF ? (t - 1 - s) : s;
-        const int b = P.bit_lo + lb;  // global index bit paired at this stage
-        for (int bf = threadIdx.x; bf < nbf; bf += blockDim.x) {
-            int i0 = ((bf >> lb) << (lb + 1)) | (bf & ((1 << lb) - 1));
-            int i1 = i0 + (1 << lb);
-            size_t g0 = base + (size_t(i0) << P.bit_lo);
-            size_t e = (g0 & ((size_t(1) << b) - 1)) << (P.log_n - 1 - b);
-            Fr u = smem_get(plo, phi, i0), v = smem_get(plo, phi, i1);
-            if (b == 0) {  // the stage that pairs neighbours: every twiddle is w^0 = 1 (1/log2 n of all products)
-                smem_put(plo, phi, i0, fr_add(u, v));
-                smem_put(plo, phi, i1, fr_sub(u, v));
-                continue;
-            }
-            Fr w = fr_load_nc(P.tw + e);
-            if (DIF) {
-                smem_put(plo, phi, i0, fr_add(u, v));
-                smem_put(plo, phi, i1, fr_mul(fr_sub(u, v), w));
-            } else {
-                Fr vw = fr_mul(v, w);
-                smem_put(plo, phi, i0, fr_add(u, vw));
-                smem_put(plo, phi, i1, fr_sub(u, vw));
-            }
+template <bool DIF>
+__global__ void __launch_bounds__(256, NTT_TILE_MINB) k_ntt_tile(const __grid_constant__ NttPass P) {
+    extern __shared__ uint4 smem[];
+    const int t = P.t, tile = 1 << t;
+    uint4 *plo = smem, *phi = smem + tile;               // the tile
+    uint4 *wlo = smem + 2 * tile, *whi = smem + 3 * tile;  // twiddles: stage with local bit lb at [2^lb - 1, 2^(lb+1) - 1)
+    uint4 *flo = smem + 4 * tile, *fhi = smem + 5 * tile;  // coset factors (first forward pass only)
+    const size_t lo_mask = (size_t(1) << P.bit_lo) - 1;
+    // blockIdx.x = tile * n_z + coset: the cosets of one tile run side by side, so the coefficient tile they all read
+    // comes out of L2 for all but the first of them
+    const int z = int(blockIdx.x % unsigned(P.n_z));
+    const size_t tile_id = blockIdx.x / unsigned(P.n_z);
+    const size_t idx_lo = tile_id & lo_mask, idx_hi = tile_id >> P.bit_lo;
+    const size_t base = (idx_hi << (P.bit_lo + t)) | idx_lo;  // + j << bit_lo
+
+    for (int k = threadIdx.x; k < tile - 1; k += blockDim.x) {
+        const int lb = 31 - __clz(k + 1), u = k + 1 - (1 << lb), b = P.bit_lo + lb;
+        const size_t e = (idx_lo + (size_t(u) << P.bit_lo)) << (P.log_n - 1 - b);
+        smem_put(wlo, whi, k, fr_load_nc(P.tw + e));
+    }
+    if (P.pow_lo) {
+        const size_t n_lo = size_t(1) << P.pow_lo_bits, n_hi = size_t(1) << (P.log_n - P.pow_lo_bits);
+        for (int j = threadIdx.x; j < tile; j += blockDim.x) {
+            const size_t g = base + (size_t(j) << P.bit_lo);
+            smem_put(flo, fhi, j, fr_mul(fr_load_nc(P.pow_lo + z * n_lo + (g & (n_lo - 1))), fr_load_nc(P.pow_hi + z * n_hi + (g >> P.pow_lo_bits))));
+        }
+    }
+    const int c0 = blockIdx.y * P.cols_per_block;
+    const int c1 = c0 + P.cols_per_block < P.width ? c0 + P.cols_per_block : P.width;
+    for (int c = c0; c < c1; c++) {
+        const Fr* src = P.src + size_t(c) * P.src_col_stride + z * P.src_z_stride;
+        Fr* dst = P.dst + size_t(c) * P.dst_col_stride + z * P.dst_z_stride;
+        __syncthreads();   // the previous column's stores have read the tile; twiddles / factors are in place
+        for (int j = threadIdx.x; j < tile; j += blockDim.x) {
+            const size_t g = base + (size_t(j) << P.bit_lo);
+            const size_t sidx = P.bitrev_load ? size_t(bitrev32(uint32_t(g), P.log_n)) : g;
+            Fr v = fr_load_nc(src + sidx);
+            if (P.pow_lo) v = fr_mul(v, smem_get(flo, fhi, j));
+            smem_put(plo, phi, j, v);
         }
         __syncthreads();
-    }
-
-    for (int j = threadIdx.x; j < tile; j += blockDim.x) {
-        size_t g = base + (size_t(j) << P.bit_lo);
-        Fr v = smem_get(plo, phi, j);
-        if (P.scale_store) v = fr_mul(v, P.scale);
-        fr_store(dst + g, v);
+        int s = 0;
+        for (; s + 1 < t; s += 2) {   // two stages per barrier
+            // DIF walks the local bits from high to low, DIT from low to high; lbB < lbA are this round's two bits
+            const int lbA = DIF ? t - 1 - s : s + 1, lbB = lbA - 1;
+            for (int q = threadIdx.x; q < (tile >> 2); q += blockDim.x) {
+                const int low = q & ((1 << lbB) - 1);
+                const int i00 = ((q >> lbB) << (lbB + 2)) | low, i01 = i00 + (1 << lbB), i10 = i00 + (1 << lbA), i11 = i10 + (1 << lbB);
+                Fr x00 = smem_get(plo, phi, i00), x01 = smem_get(plo, phi, i01), x10 = smem_get(plo, phi, i10), x11 = smem_get(plo, phi, i11);
+                const int ta = (1 << lbA) - 1, tb = (1 << lbB) - 1;
+                if (DIF) {   // bit lbA first: (x00,x10) and (x01,x11), then bit lbB: (x00,x01) and (x10,x11) share a twiddle
+                    ntt_bfly<true>(x00, x10, smem_get(wlo, whi, ta + low), false);
+                    ntt_bfly<true>(x01, x11, smem_get(wlo, whi, ta + low + (1 << lbB)), false);
+                    const bool triv = P.bit_lo + lbB == 0;   // the stage that pairs neighbours: every twiddle is 1
+                    const Fr wb = smem_get(wlo, whi, tb + low);
+                    ntt_bfly<true>(x00, x01, wb, triv);
+                    ntt_bfly<true>(x10, x11, wb, triv);
+                } else {     // bit lbB first (shared twiddle), then bit lbA
+                    const bool triv = P.bit_lo + lbB == 0;
+                    const Fr wb = smem_get(wlo, whi, tb + low);
+                    ntt_bfly<false>(x00, x01, wb, triv);
+                    ntt_bfly<false>(x10, x11, wb, triv);
+                    ntt_bfly<false>(x00, x10, smem_get(wlo, whi, ta + low), false);
+                    ntt_bfly<false>(x01, x11, smem_get(wlo, whi, ta + low + (1 << lbB)), false);
+                }
+                smem_put(plo, phi, i00, x00);
+                smem_put(plo, phi, i01, x01);
+                smem_put(plo, phi, i10, x10);
+                smem_put(plo, phi, i11, x11);
+            }
+            __syncthreads();
+        }
+        if (s < t) {   // odd number of stages: one radix-2 stage left
+            const int lb = DIF ? 0 : t - 1;
+            const bool triv = P.bit_lo + lb == 0;
+            for (int bf = threadIdx.x; bf < (tile >> 1); bf += blockDim.x) {
+                const int low = bf & ((1 << lb) - 1);
+                const int i0 = ((bf >> lb) << (lb + 1)) | low, i1 = i0 + (1 << lb);
+                Fr u = smem_get(plo, phi, i0), v = smem_get(plo, phi, i1);
+                ntt_bfly<DIF>(u, v, smem_get(wlo, whi, (1 << lb) - 1 + low), triv);
+                smem_put(plo, phi, i0, u);
+                smem_put(plo, phi, i1, v);
+            }
+            __syncthreads();
+        }
+        for (int j = threadIdx.x; j < tile; j += blockDim.x) {
+            Fr v = smem_get(plo, phi, j);
+            if (P.scale_store) v = fr_mul(v, P.scale);
+            fr_store(dst + base + (size_t(j) << P.bit_lo), v);
+        }
     }
 }
 
@@ -177,16 +231,30 @@ static void split_passes(int log_n, std::vector<int>& ts) {
     for (int i = 0; i < k; i++) ts.push_back(log_n / k + (i < log_n % k ? 1 : 0));
 }
 
-static int launch_pass(lsp_ctx* ctx, bool dif, const NttPass& P, size_t width, int n_z) {
+// Columns a block loops over: all of a small matrix, at most 8 (the coset factors and twiddles are then amortised 8 x).
+constexpr int NTT_COLS_PER_BLOCK = 8;
+
+static int launch_pass(lsp_ctx* ctx, bool dif, NttPass P, size_t width, int n_z) {
     size_t tiles = (size_t(1) << P.log_n) >> P.t;
-    int threads = 1 << (P.t > 0 ? P.t - 1 : 0);
+    P.width = int(width);
+    P.n_z = n_z;
+    P.cols_per_block = int(width < size_t(NTT_COLS_PER_BLOCK) ? width : size_t(NTT_COLS_PER_BLOCK));
+    // a matrix of few columns and few tiles would leave SMs idle: fewer columns per block then
+    while (P.cols_per_block > 1 && tiles * size_t(n_z) * ((width + P.cols_per_block - 1) / P.cols_per_block) < size_t(ctx->sm_count) * NTT_TILE_MINB)
+        P.cols_per_block = (P.cols_per_block + 1) / 2;
+    int threads = 1 << (P.t > 2 ? P.t - 2 : 0);
     if (threads < 32) threads = 32;
-    size_t smem = (size_t(2) << P.t) * sizeof(uint4);
-    dim3 grid((unsigned)tiles, (unsigned)width, (unsigned)n_z);
+    const size_t smem = (size_t(P.pow_lo ? 6 : 4) << P.t) * sizeof(uint4);
+    dim3 grid((unsigned)(tiles * size_t(n_z)), (unsigned)((width + P.cols_per_block - 1) / P.cols_per_block), 1);
+    if (!ctx->ntt_smem_opt_in) {   // opt in to > 48 KiB of dynamic shared memory, once per device
+        LSP_CUDA(ctx, cudaFuncSetAttribute(k_ntt_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (6 << NTT_MAX_T) * int(sizeof(uint4))));
+        LSP_CUDA(ctx, cudaFuncSetAttribute(k_ntt_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (6 << NTT_MAX_T) * int(sizeof(uint4))));
+        ctx->ntt_smem_opt_in = true;
+    }
     if (dif)
-        LSP_LAUNCH(ctx, k_ntt_pass<true>, grid, threads, smem, P);
+        LSP_LAUNCH(ctx, k_ntt_tile<true>, grid, threads, smem, P);
     else
-        LSP_LAUNCH(ctx, k_ntt_pass<false>, grid, threads, smem, P);
+        LSP_LAUNCH(ctx, k_ntt_tile<false>, grid, threads, smem, P);
     return LSP_OK;
 }
 
