@@ -93,7 +93,10 @@ __device__ __forceinline__ Fr smem_get(const uint4* plo, const uint4* phi, int i
 //     costs 4 products and 3 twiddle reads; in a prime field there is no cheaper radix-4 butterfly): half the barriers
 //     and half the shared-memory traffic of one stage per barrier, and two independent products in flight per thread.
 // Shared memory: tile + twiddles (+ factors) = 2 or 3 planes of 2^t x 32 bytes (96 KiB at t = 10 with factors).
-constexpr int NTT_TILE_MINB = 2;   // resident blocks per SM the kernel is compiled for (<= 128 registers at 256 threads)
+#ifndef LSP_NTT_MINB
+#define LSP_NTT_MINB 2
+#endif
+constexpr int NTT_TILE_MINB = LSP_NTT_MINB;   // resident blocks per SM the kernel is compiled for (<= 128 registers at 256 threads)
 
 template <bool DIF>
 __device__ __forceinline__ void ntt_bfly(Fr& u, Fr& v, const Fr& w, bool trivial) {

@@ -74,6 +74,23 @@ __global__ void __launch_bounds__(32) k_ch_sample(const __grid_constant__ P2Para
     Fr v = ch_sample<D>(P, ch);
     if (threadIdx.x == 0) fr_store(out, v);
 }
+// observe(vals[0..n)) then sample() in ONE launch, optionally copying the observed values to `copy_to` first (a
+// commitment on its way into the proof): what every commit-phase round does with its root.  Saves two launches and a
+// device copy per round on the latency chain of the FRI commit phase.
+template <int D>
+__global__ void __launch_bounds__(32) k_ch_observe_sample(const __grid_constant__ P2Params P, DevChallenger* ch, const __grid_constant__ ObserveList L,
+                                                          Fr* copy_to, Fr* out) {
+    if (threadIdx.x == 0)
+        for (int s = 0; s < L.n_seg; s++)
+            for (int i = 0; i < L.n[s]; i++) {
+                const Fr v = fr_load(L.p[s] + i);
+                ch_observe(ch, v);
+                if (copy_to && s == 0) fr_store(copy_to + i, v);
+            }
+    __syncwarp();
+    Fr v = ch_sample<D>(P, ch);
+    if (threadIdx.x == 0) fr_store(out, v);
+}
 // canonical integer of a Montgomery-form element: multiply by 1
 __device__ __forceinline__ Fr fr_from_mont(const Fr& a) {
     Fr one = fr_zero();
@@ -210,6 +227,17 @@ int challenger_observe_dev(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals, int 
 int challenger_sample(lsp_ctx* ctx, DevChallenger* ch, Fr* out_dev) {
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample<D>, 1, 32, 0, ctx->p2, ch, out_dev));
     return LSP_OK;
+}
+int challenger_observe_sample(lsp_ctx* ctx, DevChallenger* ch, const ObserveList& L, Fr* copy_to, Fr* out_dev) {
+    LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_observe_sample<D>, 1, 32, 0, ctx->p2, ch, L, copy_to, out_dev));
+    return LSP_OK;
+}
+int challenger_observe_sample(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals, int n, Fr* copy_to, Fr* out_dev) {
+    ObserveList L;
+    L.n_seg = 1;
+    L.p[0] = vals;
+    L.n[0] = n;
+    return challenger_observe_sample(ctx, ch, L, copy_to, out_dev);
 }
 int challenger_sample_bits(lsp_ctx* ctx, DevChallenger* ch, int bits, int n, uint32_t* idx_out) {
     LSP_DISPATCH_SBOX(ctx->p2.sbox_d, LSP_LAUNCH(ctx, k_ch_sample_bits<D>, 1, 32, 0, ctx->p2, ch, bits, n, idx_out));

@@ -214,6 +214,15 @@ int challenger_init(lsp_ctx* ctx, DevChallenger* ch);
 int challenger_observe_dev(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals, int n);
 int challenger_observe_host(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals_host, int n);
 int challenger_sample(lsp_ctx* ctx, DevChallenger* ch, Fr* out_dev);
+// observe(vals[0..n)) (copied to `copy_to` too when non-null), then sample(): one launch.  The list form observes several
+// runs of values in order (the first run is the one copied).
+struct ObserveList {
+    const Fr* p[4];
+    int n[4];
+    int n_seg;
+};
+int challenger_observe_sample(lsp_ctx* ctx, DevChallenger* ch, const Fr* vals, int n, Fr* copy_to, Fr* out_dev);
+int challenger_observe_sample(lsp_ctx* ctx, DevChallenger* ch, const ObserveList& L, Fr* copy_to, Fr* out_dev);
 // `n` successive sample_bits(bits) -> idx_out[n]
 int challenger_sample_bits(lsp_ctx* ctx, DevChallenger* ch, int bits, int n, uint32_t* idx_out);
 // grind(bits): smallest witness; observes it and consumes one sample (check_witness)

@@ -488,10 +488,14 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     ctx->phase = "quotient";
     for (size_t i = 0; i < H; i++) {
         RankState& R = st[i];
-        LSP_TRY(challenger_observe_dev(ctx, R.ch, R.sc + S_LOGN, 1));
-        LSP_TRY(challenger_observe_dev(ctx, R.ch, R.proof, 1));
-        LSP_TRY(challenger_observe_dev(ctx, R.ch, R.sc + S_PUB0, 2));
-        LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_ALPHA));
+        {   // observe(log_degree); observe(trace_commit); observe_slice(publics); alpha <- sample
+            ObserveList ol;
+            ol.n_seg = 3;
+            ol.p[0] = R.sc + S_LOGN, ol.n[0] = 1;
+            ol.p[1] = R.proof, ol.n[1] = 1;
+            ol.p[2] = R.sc + S_PUB0, ol.n[2] = 2;
+            LSP_TRY(challenger_observe_sample(ctx, R.ch, ol, nullptr, R.sc + S_ALPHA));
+        }
         LSP_TRY(P.get(&R.chunks, size_t(q) * n * 32));
         // row block b of the quotient domain (b < q) holds chunk bitrev(b); its owner computes it (the blocks of one
         // rank are adjacent: one launch)
@@ -560,8 +564,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         Fr* p_local = R.proof + 2;
         Fr* p_next = p_local + W;
         Fr* p_chunks = p_next + W;
-        LSP_TRY(challenger_observe_dev(ctx, R.ch, R.proof + 1, 1));
-        LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_ZETA));
+        LSP_TRY(challenger_observe_sample(ctx, R.ch, R.proof + 1, 1, nullptr, R.sc + S_ZETA));   // observe(quotient_commit); zeta <- sample
         LSP_LAUNCH(ctx, k_chunk_consts, 1, 32, 0, (const FieldConsts*)ctx->fc, (const Fr*)(R.sc + S_ZETA), log_n, log_q, (Fr*)nullptr, R.sc + S_ZETA_NEXT, R.sc + S_CHUNK_PT);
         // `TwoAdicFriPcs::open`: the pinned fork samples the batching challenge first and never observes the opened
         // values; later upstream observes them (trace at zeta, trace at zeta', each chunk at zeta) and samples after.
@@ -621,9 +624,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
                 Fr* top = R.fri_top + size_t(r) * 2 * G;
                 LSP_TRY(merkle_top(ctx, top, G));
                 const Fr* root = top + (2 * size_t(G) - 2);
-                LSP_CUDA(ctx, cudaMemcpyAsync(R.proof + 2 + 2 * W + q + r, root, 32, cudaMemcpyDeviceToDevice, ctx->stream));
-                LSP_TRY(challenger_observe_dev(ctx, R.ch, root, 1));
-                LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_BETA));
+                LSP_TRY(challenger_observe_sample(ctx, R.ch, root, 1, R.proof + 2 + 2 * W + q + r, R.sc + S_BETA));
                 Fr* nxt = cur[i] + local;
                 LSP_TRY(fri_fold_range(ctx, cur[i], len, size_t(R.rank) * (local / 2), local / 2, R.sc + S_BETA, nxt));
                 R.rounds[r].vec = cur[i];
@@ -660,9 +661,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
             for (int rr = r; rr < n_rounds; rr++) {
                 LSP_TRY(merkle_build_pairs(ctx, c, ln, d));
                 const Fr* root = d + (ln - 2);
-                LSP_CUDA(ctx, cudaMemcpyAsync(R.proof + 2 + 2 * W + q + rr, root, 32, cudaMemcpyDeviceToDevice, ctx->stream));
-                LSP_TRY(challenger_observe_dev(ctx, R.ch, root, 1));
-                LSP_TRY(challenger_sample(ctx, R.ch, R.sc + S_BETA));
+                LSP_TRY(challenger_observe_sample(ctx, R.ch, root, 1, R.proof + 2 + 2 * W + q + rr, R.sc + S_BETA));
                 LSP_TRY(fri_fold(ctx, c, ln, R.sc + S_BETA, c + ln));
                 R.rounds[rr].vec = c;
                 R.rounds[rr].tree.local = d;
