@@ -98,37 +98,66 @@ def perm_counts(log_n: int, w: int, log_blowup: int, q: int, log_final: int):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region, in-process through NVML (nvidia_ml_py): no
+    `nvidia-smi` child every 200 ms beside a process holding gigabytes of pinned memory.  Falls back to nvidia-smi when
+    the NVML binding is missing."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    BITS = [0x8, 0x40, 0x20, 0x4]      # nvmlClocksEventReason{HwSlowdown, HwThermalSlowdown, SwThermalSlowdown, SwPowerCap}
 
     def __init__(self, gpu_index: int):
         super().__init__(daemon=True)
         self.gpu, self.rows, self._halt = gpu_index, [], threading.Event()
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            # CUDA_VISIBLE_DEVICES may renumber devices: prefer the NVML device on the PCI bus CUDA reports for gpu_index
+            bus = getattr(torch.cuda.get_device_properties(gpu_index), "pci_bus_id", None)
+            for i in range(pynvml.nvmlDeviceGetCount() if bus is not None else 0):
+                h = pynvml.nvmlDeviceGetHandleByIndex(i)
+                if pynvml.nvmlDeviceGetPciInfo(h).bus == bus:
+                    self.handle = h
+                    break
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = self.handle = None
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                reasons = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                reasons = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            return [float(sm), float(mx)] + [bool(reasons & b) for b in self.BITS]
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                             capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().splitlines()[0].split(",")]
+        return [float(f[1]), float(f[2])] + [f[4 + i].lower().startswith("active") for i in range(4)]
 
     def run(self):
         while not self._halt.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    f = [x.strip() for x in line.split(",")]
-                    if len(f) >= 8:
-                        self.rows.append(f)
+                self.rows.append(self.sample())
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.1 if self.nvml is not None else 0.25)
 
     def stop(self):
         self._halt.set()
         self.join(timeout=6)
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if r[4 + i].lower().startswith("active")})
+        sm = sorted(r[0] for r in self.rows)
+        mx = [r[1] for r in self.rows]
+        reasons = sorted({self.NAMES[i] for r in self.rows for i in range(4) if r[2 + i]})
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(self.rows), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def measured_peaks():
@@ -242,7 +271,7 @@ class GpuWorkload:
     def __init__(self, pkg, torch, ctx, comm, args):
         self.pkg, self.ctx, self.comm, self.args = pkg, ctx, comm, args
         ab, pub, consts, diag = workload_inputs(args)     # every rank builds the same trace
-        self.inputs = (ab, pub, consts, diag)
+        self.inputs = (ab if comm is None else None, pub, consts, diag)   # the a/b columns are only needed again by the CPU leg (N = 1)
         ctx.check(ctx.lib.lsp_set_poseidon2(ctx.h, 3, args.sbox_d, 8, 22, pkg.ffi.as_u64p(consts), pkg.ffi.as_u64p(diag)),
                   "lsp_set_poseidon2")
         self.n, self.c = 1 << args.log_n, args.cols
@@ -325,7 +354,7 @@ def run_gpu(args, rank, world, local_rank):
     # ---- timed region: `value` (trace resident in HBM) --------------------------------
     # Only the dominant kernel (the Poseidon2 leaf hash: 2 launches per step) is bracketed by CUDA events here, on
     # the library's own stream; events around every one of the launches would cost ~4 % of the step.
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)       # every rank samples its own GPU through its own NVML handle (no child processes)
     sampler.start()
     launches0 = ctx.kernel_launches()
     ctx.kernel_timing(2)
