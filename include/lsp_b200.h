@@ -343,8 +343,9 @@ int lsp_comm_init_nccl(lsp_ctx* ctx, int rank, int world, const uint8_t unique_i
  * copies: the same sharded code path on a single GPU (tests, 1-GPU boxes). */
 int lsp_comm_init_local(lsp_ctx* ctx, int world, lsp_comm** out);
 void lsp_comm_destroy(lsp_comm* comm);
-/* `prove` sharded over comm's ranks (world a power of two <= 2^log_blowup).  Every rank
- * passes the same trace and receives the same proof, bit-identical to lsp_prove_permutation. */
+/* `prove` sharded over comm's ranks (world any power of two; with more ranks than the 2^log_blowup cosets a rank
+ * owns a fraction of one, at least 8 rows of it).  Every rank passes the same trace and receives the same proof,
+ * bit-identical to lsp_prove_permutation -- which is this same code with one rank. */
 int lsp_prove_permutation_sharded(lsp_comm* comm, const lsp_fri_config* fri, const uint64_t* trace, size_t rows,
                                   size_t width, const lsp_perm_air_cfg* cfgs, int n_cfgs, const uint64_t publics[2][4],
                                   uint64_t* proof_out, size_t proof_words, float* timings_ms_out);
