@@ -745,13 +745,21 @@ def shard_plan(log_n: int, log_blowup: int, world: int, rank: int) -> dict:
     """Which part of the committed matrices a rank owns: storage rows [row0, row0+rows) of the
     bit-reversed LDE = `cosets` (exponents c of shift*w_L^c) of the evaluation domain."""
     big = 1 << (log_n + log_blowup)
-    if world & (world - 1) or world > (1 << log_blowup):
-        raise BackendError(f"{world} ranks need a power of two <= 2^log_blowup = {1 << log_blowup}")
+    if world < 1 or world & (world - 1):
+        raise BackendError(f"{world} ranks: the rank count must be a power of two")
     rows = big // world
-    blocks = (1 << log_blowup) // world
-    rev = lambda x: int(format(x, f"0{log_blowup}b")[::-1], 2) if log_blowup else 0
-    return dict(row0=rank * rows, rows=rows, blocks=list(range(rank * blocks, (rank + 1) * blocks)),
-                cosets=[rev(b) for b in range(rank * blocks, (rank + 1) * blocks)])
+    rev = lambda x, bits: int(format(x, f"0{bits}b")[::-1], 2) if bits else 0
+    if world <= (1 << log_blowup):      # whole cosets
+        blocks = (1 << log_blowup) // world
+        return dict(row0=rank * rows, rows=rows, blocks=list(range(rank * blocks, (rank + 1) * blocks)),
+                    cosets=[rev(b, log_blowup) for b in range(rank * blocks, (rank + 1) * blocks)], fraction=(0, 1))
+    # more ranks than cosets: the fraction 1/S of one coset -- the trace rows k = k0 (mod S) of it, i.e. the sub-coset
+    # sigma * H_{N/S} with sigma = shift * w_L^c * w_N^k0 (host/sharded.cu, csrc/ntt.cu coset_evaluate_subblock)
+    log_s = (world >> log_blowup).bit_length() - 1
+    if log_n - log_s < 3:
+        raise BackendError(f"{world} ranks are too many for 2^{log_n} x 2^{log_blowup} rows")
+    block, sub = rank >> log_s, rank & ((1 << log_s) - 1)
+    return dict(row0=rank * rows, rows=rows, blocks=[block], cosets=[rev(block, log_blowup)], fraction=(rev(sub, log_s), 1 << log_s))
 
 
 def prove_sharded(comm: Comm, fri: FriConfig, cfgs, trace, publics, timings=None):

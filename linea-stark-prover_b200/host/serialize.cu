@@ -105,6 +105,10 @@ struct Writer {
     void u32(uint32_t v) { bytes(&v, 4); }
     void u64(uint64_t v) { bytes(&v, 8); }
     void felt(const uint64_t* mont) {  // Montgomery limbs -> canonical little-endian bytes
+        if (!p) {                          // size-only pass: nothing is read
+            n += 32;
+            return;
+        }
         static const uint64_t one[4] = {1, 0, 0, 0};
         uint64_t c[4];
         mont_mul(mont, one, c);
@@ -112,7 +116,7 @@ struct Writer {
     }
     void felts(const uint64_t* mont, size_t k, bool len_prefix) {
         if (len_prefix) u64(k);
-        for (size_t i = 0; i < k; i++) felt(mont + 4 * i);
+        for (size_t i = 0; i < k; i++) felt(mont ? mont + 4 * i : nullptr);
     }
 };
 struct Reader {
@@ -146,8 +150,8 @@ size_t write_proof(const Shape& s, const uint64_t* flat, uint8_t* out, size_t ca
     w.u32(1);
     w.u32(s.fri.log_blowup); w.u32(s.fri.log_final_poly_len); w.u32(s.fri.num_queries); w.u32(s.fri.proof_of_work_bits);
     w.u32(s.width); w.u32(s.log_q);
-    const uint64_t* f = flat;
-    auto adv = [&](size_t k) { const uint64_t* r = f; f += 4 * k; return r; };
+    size_t off = 0;   // (flat == nullptr: size-only pass, no pointer is formed)
+    auto adv = [&](size_t k) { const uint64_t* r = flat ? flat + off : nullptr; off += 4 * k; return r; };
     w.felts(adv(1), 1, false);                                   // commitments.trace
     w.felts(adv(1), 1, false);                                   // commitments.quotient_chunks
     w.felts(adv(s.width), s.width, true);                        // opened_values.trace_local
@@ -185,8 +189,7 @@ size_t write_proof(const Shape& s, const uint64_t* flat, uint8_t* out, size_t ca
 extern "C" size_t lsp_proof_serialized_bytes(uint32_t log_n, uint32_t width, uint32_t log_q, const lsp_fri_config* fri) {
     Shape s;
     if (!make_shape(log_n, width, log_q, fri, s)) return 0;
-    std::vector<uint64_t> zero(lsp_proof_words(log_n, width, log_q, fri), 0);
-    return write_proof(s, zero.data(), nullptr, 0);
+    return write_proof(s, nullptr, nullptr, 0);   // size-only pass
 }
 
 extern "C" int lsp_proof_serialize(const uint64_t* proof, size_t proof_words, uint32_t log_n, uint32_t width, uint32_t log_q,
@@ -215,6 +218,9 @@ extern "C" int lsp_proof_deserialize(const uint8_t* bytes, size_t len, uint32_t*
     Shape s;
     if (!make_shape(uint32_t(log_n64), width, log_q, &fri, s)) return LSP_ERR_PARAM;
     const size_t words = lsp_proof_words(s.log_n, width, log_q, &fri);
+    // the stream's length is a function of the shape: a header that promises anything else is malformed (and must not
+    // make a caller allocate for it)
+    if (write_proof(s, nullptr, nullptr, 0) != len) return LSP_ERR_PARAM;
     *log_n_out = s.log_n; *width_out = width; *log_q_out = log_q; *fri_out = fri;
     if (proof_words_out) *proof_words_out = words;
     if (!proof_out) return LSP_OK;                               // shape query

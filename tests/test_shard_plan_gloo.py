@@ -62,6 +62,74 @@ def _worker(rank, world, port, q):
     q.put(rank)
 
 
+def _worker_fraction(rank, world, port, q):
+    """More ranks than cosets (blowup 1, two ranks): each rank owns HALF of the one coset.  Its rows are a sub-coset: the
+    trace polynomial folded to half its degree (x^M is constant there) and evaluated on sigma * H_M; its next rows are the
+    same for p(w_N x); the subtree roots still assemble the commitment."""
+    sys.path.insert(0, str(ROOT))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import __graft_entry__ as g
+    from oracle import dft as OD
+    from oracle import field as F
+    from oracle import merkle as OM
+    from oracle import poseidon2 as OP
+    pkg = g.load_package()
+    p = OP.Poseidon2Params.from_seed(1)
+    log_n, blow = 4, 0
+    n = 1 << log_n
+    rng = F.SplitMix64(9)
+    mat = [[rng.next_fr() for _ in range(2)] for _ in range(n)]
+    plan = pkg.shard_plan(log_n, blow, world, rank)
+    k0, s = plan["fraction"]
+    assert s == world and plan["rows"] == n // s and plan["cosets"] == [0]
+    m = n // s
+    full = OD.coset_lde_batch(mat, blow, F.GENERATOR)                      # bit-reversed rows of p(g w_N^k)
+    coeffs = [OD.idft([row[c] for row in mat]) for c in range(2)]          # natural-order coefficients of each column
+    w_n = F.two_adic_generator(log_n)
+    for nxt in (0, 1):
+        sigma = F.GENERATOR * pow(w_n, k0 + nxt, F.R_MOD) % F.R_MOD
+        u = pow(sigma, m, F.R_MOD)
+        local = [[0, 0] for _ in range(m)]
+        for c in range(2):
+            a = coeffs[c]
+            folded = [sum(a[i0 + m * t] * pow(u, t, F.R_MOD) for t in range(s)) % F.R_MOD for i0 in range(m)]
+            w_m = F.two_adic_generator(log_n - (s.bit_length() - 1))
+            for mm in range(m):
+                x = sigma * pow(w_m, mm, F.R_MOD) % F.R_MOD
+                local[F.reverse_bits_len(mm, m.bit_length() - 1)][c] = sum(f * pow(x, i, F.R_MOD) for i, f in enumerate(folded)) % F.R_MOD
+        if nxt == 0:
+            assert local == full[plan["row0"]:plan["row0"] + plan["rows"]]
+            mine = local
+        else:   # the NEXT trace row of local row r: the row of `full` holding trace index k + 1
+            for r in range(m):
+                k = F.reverse_bits_len(plan["row0"] + r, log_n)
+                assert local[r] == full[F.reverse_bits_len((k + 1) % n, log_n)]
+    sub = OM.MerkleTree(p, [mine])
+    roots = [None] * world
+    dist.all_gather_object(roots, sub.root)
+    top = roots
+    while len(top) > 1:
+        top = [OP.compress(p, top[2 * i], top[2 * i + 1]) for i in range(len(top) // 2)]
+    assert top[0] == OM.MerkleTree(p, [full]).root
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put(rank)
+
+
+def test_shard_plan_fraction_of_a_coset_world2_gloo():
+    world, port = 2, 29537
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_fraction, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    for pr in procs:
+        pr.join(timeout=120)
+        assert pr.exitcode == 0
+    assert sorted(q.get() for _ in range(world)) == [0, 1]
+
+
 def test_shard_plan_world2_gloo():
     world, port = 2, 29531
     ctx = mp.get_context("spawn")
@@ -77,7 +145,12 @@ def test_shard_plan_world2_gloo():
 
 def test_shard_plan_shapes(pkg):
     import pytest
-    assert pkg.shard_plan(19, 3, 8, 3) == dict(row0=3 << 19, rows=1 << 19, blocks=[3], cosets=[6])
+    assert pkg.shard_plan(19, 3, 8, 3) == dict(row0=3 << 19, rows=1 << 19, blocks=[3], cosets=[6], fraction=(0, 1))
     assert pkg.shard_plan(4, 3, 2, 1)["cosets"] == [1, 5, 3, 7]
+    # more ranks than cosets (BASELINE configs[3]: blowup 2 on 8 GPUs): rank 5 owns quarter 1 of block 1 = coset 1, the
+    # trace rows k = 2 (mod 4) of it
+    assert pkg.shard_plan(20, 1, 8, 5) == dict(row0=5 << 18, rows=1 << 18, blocks=[1], cosets=[1], fraction=(2, 4))
     with pytest.raises(pkg.BackendError):
-        pkg.shard_plan(4, 1, 4, 0)
+        pkg.shard_plan(3, 1, 8, 0)       # fewer than 8 rows per rank
+    with pytest.raises(pkg.BackendError):
+        pkg.shard_plan(4, 1, 3, 0)
