@@ -34,6 +34,23 @@ comm = pkg.Comm.local(ctx, 4)
 sd, _ = pkg.prove_sharded(comm, pkg.FriConfig(**fri), gcfgs(cfgs), trace, [alpha, delta]).to_dict()
 comm.close()
 assert sd == gd
+# more ranks than cosets: 8 ranks on 2 cosets (fold + sub-coset NTT, next-row LDE, summed chunk shares)
+fri1 = dict(fri, log_blowup=1)
+one = pkg.prove(ctx, pkg.FriConfig(**fri1), gcfgs(cfgs), trace, [alpha, delta])
+comm = pkg.Comm.local(ctx, 8)
+assert (pkg.prove_sharded(comm, pkg.FriConfig(**fri1), gcfgs(cfgs), trace, [alpha, delta]).words == one.words).all()
+comm.close()
+# verifier, serialisation round trip, Pcs::open pieces, other field parameters
+pkg.verify(ctx, pkg.FriConfig(**fri1), gcfgs(cfgs), pkg.Proof.deserialize(one.serialize()), [alpha, delta])
+lde, co = pkg.GpuDft(ctx).coset_lde_batch(ctx.upload(trace), 1, F.GENERATOR, want_coeffs=True)
+ys = pkg.eval_at(ctx, co, 12345)
+pkg.reduce_openings(ctx, [(lde, 12345, ys), (lde, 999, pkg.eval_at(ctx, co, 999))], 77).rows()
+ctx.set_field_consts(5, pow(F.TWO_ADIC_ROOT, 3, F.R_MOD))
+ctx.set_transcript_flags(False, True)
+alt = pkg.prove(ctx, pkg.FriConfig(**fri1), gcfgs(cfgs), trace, [alpha, delta])
+pkg.verify(ctx, pkg.FriConfig(**fri1), gcfgs(cfgs), alt, [alpha, delta])
+ctx.set_field_consts(F.GENERATOR, F.TWO_ADIC_ROOT)
+ctx.set_transcript_flags()
 cfgs, trace = OT.build_trace([OT.synthetic_permutation_input(3, 1, 32)], alpha, delta, [OT.synthetic_lookup_input(4, 2, 2, 32, disabled_every=5)])
 gd, _ = pkg.prove(ctx, pkg.FriConfig(**fri), gcfgs(cfgs), trace, [alpha, delta]).to_dict()
 assert gd == OS.prove(p, OS.FriConfig(**fri), cfgs, trace, [alpha, delta])
