@@ -355,10 +355,10 @@ int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width
 // On it x^M = sigma^M =: u is constant, so p folds to degree < M:
 //     p(x) = sum_{i0 < M} x^i0 * sum_{t < 2^log_s} a[i0 + M t] u^t
 // (the "DIF pre-pass of log2(G/B) stages"), and the rest is the ordinary coset evaluation of the folded polynomial with
-// shift sigma.  `next` != 0 evaluates p(w_N * x) instead: the NEXT trace row of every point (the quotient's second operand).
+// shift sigma.
 __global__ void k_subblock_consts(const FieldConsts* __restrict__ fc, const Fr* __restrict__ shift, int log_n, int added_bits, int block,
-                                  int log_s, int sub, int next, Fr* __restrict__ out /* [sigma, u] */) {
-    const uint32_t coset = bitrev32(uint32_t(block), added_bits), k0 = bitrev32(uint32_t(sub), log_s) + (next ? 1u : 0u);
+                                  int log_s, int sub, Fr* __restrict__ out /* [sigma, u] */) {
+    const uint32_t coset = bitrev32(uint32_t(block), added_bits), k0 = bitrev32(uint32_t(sub), log_s);
     Fr sigma = fr_mul(fr_load(shift), fr_pow_u32(fr_two_adic_generator(fc, log_n + added_bits), coset));
     sigma = fr_mul(sigma, fr_pow_u32(fr_two_adic_generator(fc, log_n), k0));
     Fr u = sigma;
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(128) k_fold_coeffs(const Fr* __restrict__ coef
     }
 }
 int coset_evaluate_subblock(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift, int block, int log_s,
-                            int sub, bool next, Fr* out, size_t out_col_stride) {
+                            int sub, Fr* out, size_t out_col_stride) {
     const int log_n = ilog2(n);
     if (log_s < 0 || log_s > log_n) return set_err(ctx, LSP_ERR_PARAM, "a coset of 2^%d rows cannot be split 2^%d ways", log_n, log_s);
     const size_t m = n >> log_s;
@@ -387,7 +387,7 @@ int coset_evaluate_subblock(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t wid
     Scratch tmp(ctx);
     LSP_TRY(tmp.get((void**)&sc, 64));
     LSP_TRY(tmp.get((void**)&folded, m * width * 32));
-    LSP_LAUNCH(ctx, k_subblock_consts, 1, 1, 0, (const FieldConsts*)ctx->fc, shift, log_n, added_bits, block, log_s, sub, next ? 1 : 0, sc);
+    LSP_LAUNCH(ctx, k_subblock_consts, 1, 1, 0, (const FieldConsts*)ctx->fc, shift, log_n, added_bits, block, log_s, sub, sc);
     LSP_LAUNCH(ctx, k_fold_coeffs, grid_for(ctx, m * width, 128), 128, 0, coeffs, n, m, 1 << log_s, (const Fr*)(sc + 1), folded, width);
     return coset_evaluate_blocks(ctx, folded, m, width, 0, sc, 0, 1, out, out_col_stride);
 }

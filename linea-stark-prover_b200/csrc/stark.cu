@@ -474,7 +474,8 @@ int inverse_denominators(lsp_ctx* ctx, const Fr* z_dev, int n_points, int log_m,
 // ===========================================================================
 struct QuotientArgs {
     const Fr* lde;        // column-major, column stride = lde_rows
-    const Fr* lde_next;   // optional: p(w_N x) on the same rows (same shape); nullptr = next rows are in `lde`
+    const Fr* lde_next;   // optional: the neighbouring sub-coset's rows (same shape); nullptr = next rows are in `lde`
+    int next_log_m;       // with lde_next: log2 of the sub-coset's size, or -1 when the next row is the same local row
     size_t lde_rows;
     int log_n, log_q;
     PermCfgDev cfg;
@@ -525,8 +526,14 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
         const uint32_t i = bitrev32(uint32_t(pg), lnq);
         const uint32_t i_next = (i + q) & uint32_t(nq - 1);
         const long long p = (long long)(pg - A.p_base);   // local row
-        const long long pn = A.lde_next ? p + (long long)(A.lde_next - A.lde)          // second matrix, same row
-                                        : (long long)(size_t(bitrev32(i_next, lnq)) - A.p_base);   // same N-row block
+        long long pn;
+        if (!A.lde_next) {
+            pn = (long long)(size_t(bitrev32(i_next, lnq)) - A.p_base);   // same N-row block
+        } else {                                                          // second matrix: same point, or the following one
+            long long r = p;
+            if (A.next_log_m >= 0) r = bitrev32((bitrev32(uint32_t(p), A.next_log_m) + 1u) & ((1u << A.next_log_m) - 1u), A.next_log_m);
+            pn = r + (long long)(A.lde_next - A.lde);
+        }
         const uint32_t c = i & (q - 1);
         // x = g * w_{Nq}^i
         Fr wi = (i < nq / 2) ? fr_load_nc(A.tw_nq + i) : fr_neg(fr_load_nc(A.tw_nq + (i - nq / 2)));
@@ -547,7 +554,8 @@ __global__ void __launch_bounds__(128) k_quotient_permutation(const __grid_const
 // whole chunks).  `lde` points at storage row p_base of every column (column stride lde_rows);
 // chunk c = bitrev(block) is written to chunks + c*N.
 int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, size_t p_base, int log_n, int log_q, const PermCfgDev& cfg,
-                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks, const Fr* lde_next) {
+                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks, const Fr* lde_next,
+                               bool next_rotated) {
     int lnq = log_n + log_q;
     size_t nq = size_t(1) << lnq;
     if (lnq < 1) return set_err(ctx, LSP_ERR_PARAM, "trace of height 1 with a single quotient chunk is unsupported");
@@ -580,6 +588,7 @@ int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, siz
     QuotientArgs A;
     A.lde = lde;
     A.lde_next = lde_next;
+    A.next_log_m = (lde_next && next_rotated) ? ilog2(count) : -1;
     A.lde_rows = lde_rows;
     A.log_n = log_n;
     A.log_q = log_q;

@@ -58,9 +58,9 @@ int interpolate_columns(lsp_ctx* ctx, const Fr* in, size_t n, size_t width, Fr* 
 int coset_evaluate(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift_dev, Fr* out);
 int coset_evaluate_blocks(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift_dev, int block0,
                           int n_blocks, Fr* out, size_t out_col_stride);
-// rows [sub*M, (sub+1)*M), M = n >> log_s, of row block `block` only (a rank that owns a fraction of a coset); `next`: of p(w_N x)
+// rows [sub*M, (sub+1)*M), M = n >> log_s, of row block `block` only (a rank that owns a fraction of a coset)
 int coset_evaluate_subblock(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, int added_bits, const Fr* shift_dev, int block, int log_s,
-                            int sub, bool next, Fr* out, size_t out_col_stride);
+                            int sub, Fr* out, size_t out_col_stride);
 
 // ---- core.cu ---------------------------------------------------------------
 // device row-major (host layout) -> device column-major
@@ -242,10 +242,12 @@ int quotient_permutation(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, int log_n
                          const Fr* publics_dev, const Fr* alpha_dev, Fr* chunks /* q columns of N */);
 
 // storage rows [p0, p0 + count) of the quotient domain; `lde` points at storage row p_base.  lde_next == nullptr: the next row
-// of every row lies in the same matrix (whole cosets); else it is read from lde_next at the SAME local row (a rank that
-// owns a fraction of a coset evaluates p(w_N x) on its own points, coset_evaluate_subblock(next)).
+// of every row lies in the same matrix (whole cosets).  Else the range is a sub-coset of `count` points (a rank that owns a
+// fraction of a coset) and the next rows are those of the neighbouring sub-coset, held in lde_next (same shape): at the same
+// local row, or -- next_rotated, the neighbour being the residue that wrapped to 0 -- at the row of the following point.
 int quotient_permutation_range(lsp_ctx* ctx, const Fr* lde, size_t lde_rows, size_t p_base, int log_n, int log_q, const PermCfgDev& cfg,
-                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks, const Fr* lde_next = nullptr);
+                               const Fr* publics_dev, const Fr* alpha_dev, size_t p0, size_t count, Fr* chunks, const Fr* lde_next = nullptr,
+                               bool next_rotated = false);
 
 // y[c] = sum_k coeffs[c][k] * z^k
 int eval_columns_at(lsp_ctx* ctx, const Fr* coeffs, size_t n, size_t width, const Fr* z_dev, Fr* y_dev);

@@ -41,6 +41,10 @@ struct NcclApi {
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -59,7 +63,12 @@ NcclApi* load_nccl() {
     *(void**)&api.Broadcast = dlsym(h, "ncclBroadcast");
     *(void**)&api.AllReduce = dlsym(h, "ncclAllReduce");
     *(void**)&api.GetErrorString = dlsym(h, "ncclGetErrorString");
-    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.Broadcast || !api.AllReduce) {
+    *(void**)&api.Send = dlsym(h, "ncclSend");
+    *(void**)&api.Recv = dlsym(h, "ncclRecv");
+    *(void**)&api.GroupStart = dlsym(h, "ncclGroupStart");
+    *(void**)&api.GroupEnd = dlsym(h, "ncclGroupEnd");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.AllGather || !api.Broadcast || !api.AllReduce || !api.Send ||
+        !api.Recv || !api.GroupStart || !api.GroupEnd) {
         api.lib = nullptr;
         return nullptr;
     }
@@ -108,6 +117,25 @@ int coll_broadcast(lsp_comm* cm, const std::vector<int>& ranks, int root, const 
         return LSP_OK;
     }
     LSP_NCCL(ctx, nccl_api()->Broadcast(buf[0], buf[0], bytes / 8, ncclUint64, root, ((ncclComm_t)cm->nccl), ctx->stream));
+    return LSP_OK;
+}
+
+// Point-to-point: hosted rank i sends send[i] to rank send_to[i] and receives recv[i] from rank recv_from[i] (-1: takes no
+// part).  Local mode: a device copy from the sender's buffer (send[] is indexed by global rank there).
+int coll_sendrecv(lsp_comm* cm, const std::vector<int>& ranks, const std::vector<int>& send_to, const std::vector<int>& recv_from,
+                  const std::vector<const void*>& send, const std::vector<void*>& recv, size_t bytes) {
+    lsp_ctx* ctx = cm->ctx;
+    if (cm->local) {
+        for (size_t i = 0; i < ranks.size(); i++)
+            if (recv_from[i] >= 0)
+                LSP_CUDA(ctx, cudaMemcpyAsync(recv[i], send[size_t(recv_from[i])], bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        return LSP_OK;
+    }
+    if (send_to[0] < 0 && recv_from[0] < 0) return LSP_OK;
+    LSP_NCCL(ctx, nccl_api()->GroupStart());
+    if (send_to[0] >= 0) LSP_NCCL(ctx, nccl_api()->Send(send[0], bytes / 8, ncclUint64, send_to[0], ((ncclComm_t)cm->nccl), ctx->stream));
+    if (recv_from[0] >= 0) LSP_NCCL(ctx, nccl_api()->Recv(recv[0], bytes / 8, ncclUint64, recv_from[0], ((ncclComm_t)cm->nccl), ctx->stream));
+    LSP_NCCL(ctx, nccl_api()->GroupEnd());
     return LSP_OK;
 }
 
@@ -384,9 +412,9 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     const size_t L = size_t(1) << log_l, Lr = L >> log_g;
     const int Bs = (1 << log_b) >> log_g;  // whole cosets (row blocks of N) per rank; 0 when a rank owns a fraction of one
     // this rank's rows of a committed matrix, from its coefficients: whole cosets, or the sub-coset of one
-    auto lde_local = [&](const Fr* coeffs, size_t width, const Fr* shift_dev, int rank, bool next, Fr* out) -> int {
+    auto lde_local = [&](const Fr* coeffs, size_t width, const Fr* shift_dev, int rank, Fr* out) -> int {
         if (log_s == 0) return coset_evaluate_blocks(ctx, coeffs, n, width, log_b, shift_dev, rank * Bs, Bs, out, Lr);
-        return coset_evaluate_subblock(ctx, coeffs, n, width, log_b, shift_dev, rank >> log_s, log_s, rank & ((1 << log_s) - 1), next, out, Lr);
+        return coset_evaluate_subblock(ctx, coeffs, n, width, log_b, shift_dev, rank >> log_s, log_s, rank & ((1 << log_s) - 1), out, Lr);
     };
     const int n_rounds = log_n - int(fri->log_final_poly_len);
     const int log_f = log_b + int(fri->log_final_poly_len);
@@ -459,7 +487,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_TRY(P.get(&R.top_t, 2 * size_t(G) * 32));
         LSP_TRY(P.get(&R.cols_t, W * sizeof(Fr*)));
         // ---- commit to trace data: this rank's cosets only ------------------------------------------
-        LSP_TRY(lde_local(coef_t, W, R.sc + S_GEN, R.rank, false, R.lde_t));
+        LSP_TRY(lde_local(coef_t, W, R.sc + S_GEN, R.rank, R.lde_t));
     }
     mark();  // 1
     auto commit_sharded = [&](auto lde_of, auto cols_of, auto dig_of, auto top_of, int width_cols, size_t proof_slot) -> int {
@@ -505,16 +533,37 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
                 LSP_TRY(quotient_permutation_range(ctx, R.lde_t, Lr, size_t(b0) * n, log_n, log_q, cfg_dev, R.sc + S_PUB0, R.sc + S_ALPHA,
                                                    size_t(b0) * n, size_t(b1 - b0) * n, R.chunks));
         } else {
-            // A fraction of a coset: the next row of a row is NOT among this rank's rows (adjacent trace rows are far
-            // apart in bit-reversed order).  The rank evaluates p(w_N x) on its own points instead -- one more local LDE
-            // for the ranks inside the quotient domain -- and every rank's scattered share of a chunk is summed below.
             LSP_CUDA(ctx, cudaMemsetAsync(R.chunks, 0, size_t(q) * n * 32, ctx->stream));
-            if ((R.rank >> log_s) < q) {
-                LSP_TRY(P.get(&R.lde_next, Lr * W * 32));
-                LSP_TRY(lde_local(coef_t, W, R.sc + S_GEN, R.rank, true, R.lde_next));
-                LSP_TRY(quotient_permutation_range(ctx, R.lde_t, Lr, size_t(R.rank) * Lr, log_n, log_q, cfg_dev, R.sc + S_PUB0, R.sc + S_ALPHA,
-                                                   size_t(R.rank) * Lr, Lr, R.chunks, R.lde_next));
-            }
+            if ((R.rank >> log_s) < q) LSP_TRY(P.get(&R.lde_next, Lr * W * 32));
+        }
+    }
+    if (log_s > 0) {
+        // A fraction of a coset: the next row of a row is NOT among this rank's rows (adjacent trace rows are far apart in
+        // bit-reversed order).  A rank holds the trace rows k = k0 (mod S) of its coset, so ALL its next rows are the rows of
+        // ONE neighbour, the rank with residue k0 + 1 (same local row; rotated by one evaluation point when k0 + 1 wraps to 0):
+        // the ranks of a quotient-domain coset pass their local LDE one step round the ring (NVLink send/recv: Lr*W*32 bytes,
+        // a quarter of the time of evaluating p(w_N x) locally), and every rank's scattered share of a chunk is summed below.
+        const int S = 1 << log_s;
+        auto rank_of = [&](int block, int k0) { return block * S + int(bitrev_host(uint32_t(k0), log_s)); };
+        std::vector<int> send_to(H, -1), recv_from(H, -1);
+        std::vector<const void*> send(cm->local ? size_t(G) : H, nullptr);
+        std::vector<void*> recv(H, nullptr);
+        for (size_t i = 0; i < H; i++) {
+            RankState& R = st[i];
+            const int block = R.rank >> log_s, k0 = int(bitrev_host(uint32_t(R.rank & (S - 1)), log_s));
+            send[cm->local ? size_t(R.rank) : i] = R.lde_t;
+            if (block >= q) continue;
+            send_to[i] = rank_of(block, (k0 + S - 1) & (S - 1));
+            recv_from[i] = rank_of(block, (k0 + 1) & (S - 1));
+            recv[i] = R.lde_next;
+        }
+        LSP_TRY(coll_sendrecv(cm, ranks, send_to, recv_from, send, recv, Lr * W * 32));
+        for (size_t i = 0; i < H; i++) {
+            RankState& R = st[i];
+            const int block = R.rank >> log_s, k0 = int(bitrev_host(uint32_t(R.rank & (S - 1)), log_s));
+            if (block >= q) continue;
+            LSP_TRY(quotient_permutation_range(ctx, R.lde_t, Lr, size_t(R.rank) * Lr, log_n, log_q, cfg_dev, R.sc + S_PUB0, R.sc + S_ALPHA,
+                                               size_t(R.rank) * Lr, Lr, R.chunks, R.lde_next, /*next_rotated=*/k0 == S - 1));
         }
     }
     if (log_s > 0) {  // disjoint shares + zeros: an integer sum assembles every chunk on every rank
@@ -551,7 +600,7 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
         LSP_LAUNCH(ctx, k_chunk_consts, 1, 32, 0, (const FieldConsts*)ctx->fc, (const Fr*)nullptr, log_n, log_q, R.sc + S_CHUNK_SHIFT, (Fr*)nullptr, (Fr*)nullptr);
         LSP_TRY(interpolate_columns(ctx, R.chunks, n, q, R.coef_q));
         for (int c = 0; c < q; c++)
-            LSP_TRY(lde_local(R.coef_q + size_t(c) * n, 1, R.sc + S_CHUNK_SHIFT + c, R.rank, false, R.lde_q + size_t(c) * Lr));
+            LSP_TRY(lde_local(R.coef_q + size_t(c) * n, 1, R.sc + S_CHUNK_SHIFT + c, R.rank, R.lde_q + size_t(c) * Lr));
     }
     LSP_TRY(commit_sharded([](RankState& R) { return R.lde_q; }, [](RankState& R) { return R.cols_q; }, [](RankState& R) { return R.dig_q; },
                            [](RankState& R) { return R.top_q; }, q, 1));

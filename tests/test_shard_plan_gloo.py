@@ -64,8 +64,8 @@ def _worker(rank, world, port, q):
 
 def _worker_fraction(rank, world, port, q):
     """More ranks than cosets (blowup 1, two ranks): each rank owns HALF of the one coset.  Its rows are a sub-coset: the
-    trace polynomial folded to half its degree (x^M is constant there) and evaluated on sigma * H_M; its next rows are the
-    same for p(w_N x); the subtree roots still assemble the commitment."""
+    trace polynomial folded to half its degree (x^M is constant there) and evaluated on sigma * H_M; its next rows are its
+    ring neighbour's rows; the subtree roots still assemble the commitment."""
     sys.path.insert(0, str(ROOT))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -87,24 +87,29 @@ def _worker_fraction(rank, world, port, q):
     full = OD.coset_lde_batch(mat, blow, F.GENERATOR)                      # bit-reversed rows of p(g w_N^k)
     coeffs = [OD.idft([row[c] for row in mat]) for c in range(2)]          # natural-order coefficients of each column
     w_n = F.two_adic_generator(log_n)
-    for nxt in (0, 1):
-        sigma = F.GENERATOR * pow(w_n, k0 + nxt, F.R_MOD) % F.R_MOD
-        u = pow(sigma, m, F.R_MOD)
-        local = [[0, 0] for _ in range(m)]
-        for c in range(2):
-            a = coeffs[c]
-            folded = [sum(a[i0 + m * t] * pow(u, t, F.R_MOD) for t in range(s)) % F.R_MOD for i0 in range(m)]
-            w_m = F.two_adic_generator(log_n - (s.bit_length() - 1))
-            for mm in range(m):
-                x = sigma * pow(w_m, mm, F.R_MOD) % F.R_MOD
-                local[F.reverse_bits_len(mm, m.bit_length() - 1)][c] = sum(f * pow(x, i, F.R_MOD) for i, f in enumerate(folded)) % F.R_MOD
-        if nxt == 0:
-            assert local == full[plan["row0"]:plan["row0"] + plan["rows"]]
-            mine = local
-        else:   # the NEXT trace row of local row r: the row of `full` holding trace index k + 1
-            for r in range(m):
-                k = F.reverse_bits_len(plan["row0"] + r, log_n)
-                assert local[r] == full[F.reverse_bits_len((k + 1) % n, log_n)]
+    sigma = F.GENERATOR * pow(w_n, k0, F.R_MOD) % F.R_MOD
+    u = pow(sigma, m, F.R_MOD)
+    log_m = m.bit_length() - 1
+    mine = [[0, 0] for _ in range(m)]
+    for c in range(2):
+        a = coeffs[c]
+        folded = [sum(a[i0 + m * t] * pow(u, t, F.R_MOD) for t in range(s)) % F.R_MOD for i0 in range(m)]
+        w_m = F.two_adic_generator(log_m)
+        for mm in range(m):
+            x = sigma * pow(w_m, mm, F.R_MOD) % F.R_MOD
+            mine[F.reverse_bits_len(mm, log_m)][c] = sum(f * pow(x, i, F.R_MOD) for i, f in enumerate(folded)) % F.R_MOD
+    assert mine == full[plan["row0"]:plan["row0"] + plan["rows"]]
+    # The quotient pairs every row with its NEXT trace row: those are the rows of ONE neighbour, the rank of residue
+    # k0 + 1 -- at the same local row, or at the row of the following point when the residue wrapped to 0.  One ring step.
+    everyone = [None] * world
+    dist.all_gather_object(everyone, (k0, mine))
+    theirs = dict(everyone)[(k0 + 1) % s]
+    rotated = k0 == s - 1
+    for r in range(m):
+        k = F.reverse_bits_len(plan["row0"] + r, log_n)
+        want = full[F.reverse_bits_len((k + 1) % n, log_n)]
+        rr = F.reverse_bits_len((F.reverse_bits_len(r, log_m) + 1) % m, log_m) if rotated else r
+        assert theirs[rr] == want
     sub = OM.MerkleTree(p, [mine])
     roots = [None] * world
     dist.all_gather_object(roots, sub.root)
