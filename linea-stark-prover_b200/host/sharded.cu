@@ -448,24 +448,19 @@ extern "C" int lsp_prove_air_sharded_dev(lsp_comm* cm, const lsp_fri_config* fri
     LSP_TRY(upload_air_cfgs(ctx, lookups, n_lookups, cfgs, n_cfgs, W, &cfg_dev, &cfg_blob));
     P.ptrs.push_back(cfg_blob);
     Fr* coef_t = nullptr;
-    LSP_TRY(P.get(&coef_t, n * W * 32));
+    // Every rank needs all coefficients, but not to compute them all: over NCCL each interpolates `per` of the columns and ONE
+    // in-place all-gather over NVLink completes the matrix (W*N*32 bytes in total) instead of G redundant inverse NTTs.  The
+    // buffer is padded to per*G columns so that every rank contributes the same count (the padding is never read).
+    const size_t per = (W + size_t(G) - 1) / size_t(G);
+    LSP_TRY(P.get(&coef_t, n * per * size_t(G) * 32));
     mark();  // 0
     ctx->phase = "commit_trace";
     if (!cm->local && G > 1) {
-        // Every rank needs all coefficients, but not to compute them all: each interpolates its slice of the columns
-        // and the slices are broadcast over NVLink (W*N*32 bytes in total) instead of G redundant inverse NTTs.
-        const size_t per = (W + size_t(G) - 1) / size_t(G);
-        for (int r = 0; r < G; r++) {
-            const size_t c0 = std::min(W, size_t(r) * per), c1 = std::min(W, c0 + per);
-            if (c1 == c0) continue;
-            if (r == cm->rank) LSP_TRY(interpolate_columns(ctx, tr->d + c0 * n, n, c1 - c0, coef_t + c0 * n));
-        }
-        for (int r = 0; r < G; r++) {
-            const size_t c0 = std::min(W, size_t(r) * per), c1 = std::min(W, c0 + per);
-            if (c1 == c0) continue;
-            std::vector<void*> buf{coef_t + c0 * n};
-            LSP_TRY(coll_broadcast(cm, ranks, r, buf, (c1 - c0) * n * 32));
-        }
+        const size_t c0 = std::min(W, size_t(cm->rank) * per), c1 = std::min(W, c0 + per);
+        if (c1 > c0) LSP_TRY(interpolate_columns(ctx, tr->d + c0 * n, n, c1 - c0, coef_t + c0 * n));
+        std::vector<const void*> send{coef_t + size_t(cm->rank) * per * n};
+        std::vector<void*> recv{coef_t};
+        LSP_TRY(coll_allgather(cm, ranks, send, recv, per * n * 32));   // in place: send == recv + rank * count
     } else {
         LSP_TRY(interpolate_columns(ctx, tr->d, n, W, coef_t));
     }
