@@ -29,12 +29,30 @@ def main():
     log_n = int(os.environ.get("LSP_LOG_N", "12"))
     rng = F.SplitMix64(3)
     alpha, delta = rng.next_fr(), rng.next_fr()
-    cfgs, trace = OT.build_trace([OT.synthetic_permutation_input(9, 2, 1 << log_n)], alpha, delta)
-    gc = [pkg.AirPermutationConfig(c.a_columns_ids, c.b_columns_ids, c.b_inverse_id, c.check_id) for c in cfgs]
-    fri = pkg.FriConfig(num_queries=21)
-    sharded = pkg.prove_sharded(comm, fri, gc, trace, [alpha, delta])
-    single = pkg.prove(ctx, fri, gc, trace, [alpha, delta])
-    ok = np.array_equal(sharded.words, single.words)
+    oks = []
+    # (1) the permutation AIR; (2) a lookup + permutation AIR of ODD width (15 + 4: the coefficient all-gather pads the matrix
+    # to a multiple of the rank count), 4 quotient chunks; (3) blowup 2 -- with 4 or 8 ranks: more ranks than cosets (the
+    # ring exchange of next rows and the summed chunk shares over NCCL)
+    cases = [([OT.synthetic_permutation_input(9, 2, 1 << log_n)], [], dict(num_queries=21)),
+             ([OT.synthetic_permutation_input(10, 1, 1 << (log_n - 2))], [OT.synthetic_lookup_input(11, 2, 2, 1 << (log_n - 2), disabled_every=7)],
+              dict(num_queries=9)),
+             ([OT.synthetic_permutation_input(12, 3, 1 << (log_n - 1))], [], dict(log_blowup=1, num_queries=13))]
+    for perms, lookups, fri_kw in cases:
+        cfgs, trace = OT.build_trace(perms, alpha, delta, lookups)
+        gc = []
+        for c in cfgs:
+            if hasattr(c, "occurrences_id"):
+                gc.append(pkg.AirLookupConfig(c.a_columns_ids, c.b_columns_ids, c.a_filter_id, c.b_filter_id, c.a_inverses_id, c.b_inverses_id,
+                                              c.occurrences_id, c.check_id))
+            else:
+                gc.append(pkg.AirPermutationConfig(c.a_columns_ids, c.b_columns_ids, c.b_inverse_id, c.check_id))
+        fri = pkg.FriConfig(**fri_kw)
+        single = pkg.prove(ctx, fri, gc, trace, [alpha, delta])
+        sharded = pkg.prove_sharded(comm, fri, gc, trace, [alpha, delta])                 # host trace: every rank uploads its rows
+        dev = ctx.upload(trace)
+        sharded_dev = pkg.prove_sharded(comm, fri, gc, dev, [alpha, delta])               # trace already on every device
+        oks.append(np.array_equal(sharded.words, single.words) and np.array_equal(sharded_dev.words, single.words))
+    ok = all(oks)
     flags = [None] * world
     dist.all_gather_object(flags, bool(ok))
     comm.close()

@@ -59,7 +59,8 @@ def test_sharded_rejects_too_many_ranks(pkg, gctx):
 
 
 def test_sharded_nccl_two_gpus(pkg):
-    """Real NCCL path; needs two devices (the 1-GPU box covers the same code via the local communicator)."""
+    """Real NCCL path on every device of the box (2, 4 or 8 ranks; the 1-GPU box covers the same code via the local
+    communicator): permutation AIR, an odd-width lookup AIR, and a blowup-2 case that has more ranks than cosets from 4 up."""
     import subprocess
     import sys
     import torch
@@ -67,7 +68,9 @@ def test_sharded_nccl_two_gpus(pkg):
         pytest.skip("needs >= 2 GPUs")
     from pathlib import Path
     script = Path(__file__).parent / "run_sharded_nccl.py"
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+    n = torch.cuda.device_count()
+    n = 8 if n >= 8 else 4 if n >= 4 else 2
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
                         "127.0.0.1", "--master-port", "29517", str(script)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "sharded nccl ok" in r.stdout
