@@ -38,3 +38,27 @@ def test_product_never_imports_oracle():
     for path in (ROOT / "linea-stark-prover_b200").rglob("*"):
         if path.suffix in {".py", ".cu", ".cuh", ".cpp", ".hpp", ".h"}:
             assert not pat.search(path.read_text()), path
+
+
+def test_quotient_degree_is_derived_like_the_symbolic_pass(pkg):
+    """`get_log_quotient_degree` (SURVEY.md A.8): the library derives it from `LineaAIR::eval` on symbolic degrees (host only,
+    no GPU), as the oracle does -- not from a table keyed on "has a lookup"."""
+    import ctypes as C
+
+    from oracle import air as OA
+    lib = pkg.ffi.load()
+    cases = [[OA.AirPermutationConfig.standard(1)], [OA.AirPermutationConfig.standard(6)],
+             [OA.AirLookupConfig.standard(1, 1, 1)], [OA.AirLookupConfig.standard(2, 3, 2)],
+             [OA.AirLookupConfig.standard(2, 2, 2), OA.AirPermutationConfig.standard(3)]]
+    for cfgs in cases:
+        lk = [c for c in cfgs if isinstance(c, OA.AirLookupConfig)]
+        pm = [c for c in cfgs if not isinstance(c, OA.AirLookupConfig)]
+        larr = (pkg.ffi.LookupAirCfg * max(1, len(lk)))()
+        parr = (pkg.ffi.PermAirCfg * max(1, len(pm)))()
+        for i, c in enumerate(lk):
+            larr[i].n_a_cols, larr[i].n_tables, larr[i].n_b_cols = len(c.a_columns_ids), len(c.b_columns_ids), len(c.b_columns_ids[0])
+        for i, c in enumerate(pm):
+            parr[i].n_cols = len(c.a_columns_ids)
+        got = lib.lsp_air_log_quotient_degree_cfg(larr, len(lk), parr, len(pm))
+        assert got == OA.log_quotient_degree(cfgs) == lib.lsp_air_log_quotient_degree(len(lk), len(pm)), cfgs
+    assert lib.lsp_air_log_quotient_degree_cfg(None, 1, None, 0) < 0          # a count without its configs is an error
