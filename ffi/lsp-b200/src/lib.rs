@@ -213,7 +213,9 @@ where SC: StarkGenericConfig<Challenge = Val>, SC::Pcs: Pcs<Val, SC::Challenger,
 
 /// The flat array `lsp_prove_*` writes -> `p3_uni_stark::Proof`.  FORK: field names as upstream of
 /// the era (`Proof{commitments, opened_values, opening_proof, degree_bits}`, `FriProof{commit_phase_commits, query_proofs,
-/// final_poly, pow_witness}`, `QueryProof{input_proof, commit_phase_openings}`).
+/// final_poly, pow_witness}`, `QueryProof{input_proof, commit_phase_openings}`).  FORK: upstream declares `Proof`'s fields
+/// `pub(crate)`; unless the fork exposes them, build the struct through its `Deserialize` impl instead (serialise the parts
+/// assembled here with the same serde format and read them back as `Proof<SC>`) -- the field values are the ones below.
 pub fn proof_from_flat<SC: StarkGenericConfig<Challenge = Val>>(flat: &[Val], log_n: usize, w: usize, q: usize, f: &sys::lsp_fri_config) -> Proof<SC>
 where SC::Pcs: Pcs<Val, SC::Challenger, Commitment = Hash<Val, Val, 1>, Proof = FriProof<Val, GpuMmcs<'static>, Val, Vec<BatchOpening<Val, GpuMmcs<'static>>>>> {
     let (log_l, rounds) = (log_n + f.log_blowup as usize, log_n - f.log_final_poly_len as usize);

@@ -62,3 +62,31 @@ def test_quotient_degree_is_derived_like_the_symbolic_pass(pkg):
         got = lib.lsp_air_log_quotient_degree_cfg(larr, len(lk), parr, len(pm))
         assert got == OA.log_quotient_degree(cfgs) == lib.lsp_air_log_quotient_degree(len(lk), len(pm)), cfgs
     assert lib.lsp_air_log_quotient_degree_cfg(None, 1, None, 0) < 0          # a count without its configs is an error
+
+
+def test_rust_bindings_declare_existing_symbols_with_the_headers_arity():
+    """`ffi/lsp-b200-sys/src/lib.rs` cannot be compiled here (no rustc): at least every `pub fn lsp_*` it declares must exist
+    in `include/lsp_b200.h` with the same number of parameters, and the repr(C) structs must list the header's fields in order."""
+    import re
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    header = re.sub(r"/\*.*?\*/", "", (root / "include" / "lsp_b200.h").read_text(), flags=re.S)
+    rust = re.sub(r"//.*", "", (root / "ffi" / "lsp-b200-sys" / "src" / "lib.rs").read_text())
+
+    def arity(params):
+        params = params.strip()
+        return 0 if params in ("", "void") else len([p for p in re.split(r",(?![^\[]*\])", params) if p.strip()])
+
+    c_fns = {m.group(1): arity(m.group(2)) for m in re.finditer(r"\b(lsp_\w+)\s*\(([^;{]*?)\)\s*;", header, flags=re.S)}
+    r_fns = {m.group(1): arity(m.group(2)) for m in re.finditer(r"pub fn (lsp_\w+)\s*\((.*?)\)\s*(?:->[^;]+)?;", rust, flags=re.S)}
+    assert len(r_fns) >= 40
+    for name, n in r_fns.items():
+        assert name in c_fns, f"{name} is not declared in include/lsp_b200.h"
+        assert c_fns[name] == n, f"{name}: {n} parameters in the Rust binding, {c_fns[name]} in the header"
+    # struct field order
+    for c_name in ("lsp_fri_config", "lsp_perm_air_cfg", "lsp_lookup_air_cfg"):
+        c_body = re.search(r"typedef struct \{([^{}]*)\}\s*" + c_name + r"\s*;", header).group(1)
+        c_fields = [re.findall(r"(\w+)\s*$", f.strip())[0] for f in c_body.split(";") if f.strip()]
+        r_body = re.search(r"pub struct " + c_name + r"\s*\{(.*?)\}", rust, flags=re.S).group(1)
+        r_fields = re.findall(r"pub (\w+)\s*:", r_body)
+        assert c_fields == r_fields, (c_name, c_fields, r_fields)
