@@ -127,3 +127,45 @@ def test_c_port_reproduces_the_frozen_rejection_reasons(p2params):
         bad = words.copy()
         bad[word] ^= np.uint64(1 << bit)
         assert cport.verify_limbs(fri, case["log_n"], w, cfgs, pub, bad) == code, (word, bit)
+
+
+def _round2():
+    import json
+    from pathlib import Path
+    return json.loads((Path(__file__).parent / "golden" / "golden_round2_v1.json").read_text())
+
+
+def _fnv(words):
+    h = 0xcbf29ce484222325
+    for w in words.tolist():
+        h = ((h ^ w) * 0x100000001b3) & 0xFFFFFFFFFFFFFFFF
+    return f"{h:016x}"
+
+
+def test_round2_fixture_fork_parameters_and_serialised_proof(pkg, p2params):
+    """golden_round2_v1.json: the C port reproduces the proof hash under every non-default fork-only parameter, and the
+    library's serialiser writes the committed bytes of the default-parameter proof (and reads them back)."""
+    import numpy as np
+    from oracle import air as OA
+    from oracle import cport
+    from oracle import field as F
+    from oracle import stark as OS
+    from tests.test_oracle_params import small_case
+    g = _round2()
+    cport.set_poseidon2(p2params)
+    fri = OS.FriConfig(**g["fri"])
+    cfgs, trace, publics = small_case(seed=31, log_n=4, c=2)
+    try:
+        for name, v in g["params"].items():
+            cport.set_field_consts(int(v["generator"], 16), int(v["two_adic_root"], 16))
+            cport.set_transcript_flags(v["alpha_before_openings"], v["observe_opened_values"])
+            words = cport.prove(fri, cfgs, trace, publics)
+            assert _fnv(words) == v["fnv1a64"], name
+            assert F.from_mont_limbs(words[:4]) == int(v["trace_commit"], 16), name
+            if name == "default":
+                proof = pkg.Proof(words, 4, OA.air_width(cfgs), OA.log_quotient_degree(cfgs), pkg.FriConfig(**g["fri"]))
+                assert proof.serialize().hex() == g["serialized_hex"]
+                assert pkg.Proof.deserialize(bytes.fromhex(g["serialized_hex"])).to_dict()[0] == proof.to_dict()[0]
+    finally:
+        cport.set_field_consts(F.GENERATOR, F.TWO_ADIC_ROOT)
+        cport.set_transcript_flags()

@@ -65,3 +65,25 @@ def test_device_verifier_reproduces_the_frozen_rejection_reasons(pkg, gctx):
         bad = words.copy()
         bad[word] ^= np.uint64(1 << bit)
         assert pkg.verify_code(gctx, fri, g, bad, publics, case["log_n"], w) == code, (word, bit)
+
+
+def test_round2_fixture_on_the_device(pkg, p2params):
+    """golden_round2_v1.json on the GPU: the proof hash under every non-default fork-only parameter, and a proof rebuilt from
+    the committed serialised bytes is accepted by the device verifier."""
+    from oracle import field as F
+    from tests.test_golden import _fnv, _round2
+    from tests.test_oracle_params import small_case
+    g = _round2()
+    ctx = pkg.Context(0)
+    ctx.set_poseidon2(p2params.sbox_d, p2params.rounds_f, p2params.rounds_p, p2params.flat_constants(), p2params.internal_diag_m1)
+    cfgs, trace, publics = small_case(seed=31, log_n=4, c=2)
+    gc = [pkg.AirPermutationConfig(c.a_columns_ids, c.b_columns_ids, c.b_inverse_id, c.check_id) for c in cfgs]
+    fri = pkg.FriConfig(**g["fri"])
+    for name, v in g["params"].items():
+        ctx.set_field_consts(int(v["generator"], 16), int(v["two_adic_root"], 16))
+        ctx.set_transcript_flags(v["alpha_before_openings"], v["observe_opened_values"])
+        assert _fnv(pkg.prove(ctx, fri, gc, trace, publics).words) == v["fnv1a64"], name
+    ctx.set_field_consts(F.GENERATOR, F.TWO_ADIC_ROOT)
+    ctx.set_transcript_flags()
+    pkg.verify(ctx, fri, gc, pkg.Proof.deserialize(bytes.fromhex(g["serialized_hex"])), publics)
+    ctx.close()
