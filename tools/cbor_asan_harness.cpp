@@ -1,6 +1,7 @@
 // AddressSanitizer harness for the CBOR reader (host/cbor.cu): every entry point, serial and with the parallel pre-pass
 // forced on, over files given on the command line (each copied into an exact-size heap block so that a read past the end
-// is caught).  Inputs: tests/test_cbor_fuzz.py:_mutations writes them; last run: 3012 mutated files, no report.
+// is caught).  Inputs: tests/test_cbor_fuzz.py:_mutations writes them (+ deep-nesting files); last run (round 2, incl. the
+// padded `_decode` / `_read_rows` entry points and 100 000-deep nested values): see profiles/r3q_cbor_asan.log.
 //   nvcc -O1 -g -std=c++17 -Xcompiler -fsanitize=address,-fno-omit-frame-pointer -o cbor_asan \
 //        linea-stark-prover_b200/host/cbor.cu tools/cbor_asan_harness.cpp -lcudart
 //   ASAN_OPTIONS=detect_leaks=0:protect_shadow_gap=0 ./cbor_asan in/*.bin
@@ -32,7 +33,14 @@ int main(int argc, char** argv) {
             if (lsp_cbor_permutation_shape(blob, raw.size(), &r2, &c2, name, sizeof name) == 0 && r2 && c2) {
                 std::vector<uint8_t> o(r2 * 2 * c2 * 32);
                 lsp_cbor_permutation_decode(blob, raw.size(), o.data(), r2, c2);
+                // push_traces' resize: a taller common height (exact-size buffer: a write past the padded rows is caught)
+                std::vector<uint8_t> taller((r2 + 5) * 2 * c2 * 32);
+                lsp_cbor_permutation_decode(blob, raw.size(), taller.data(), r2 + 5, c2);
             }
+            out = nullptr;
+            if (lsp_cbor_permutation_read_rows(blob, raw.size(), 37, &rows, &a, name, sizeof name, &out) == 0) lsp_host_free(out);
+            out = nullptr;
+            if (lsp_cbor_lookup_read_rows(blob, raw.size(), 37, &rows, &a, &t, &b, name, sizeof name, &out) == 0) lsp_host_free(out);
         }
         free(blob);
     }
