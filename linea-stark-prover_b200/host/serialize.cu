@@ -211,7 +211,11 @@ extern "C" int lsp_proof_deserialize(const uint8_t* bytes, size_t len, uint32_t*
     lsp_fri_config fri;
     fri.log_blowup = r.u32(); fri.log_final_poly_len = r.u32(); fri.num_queries = r.u32(); fri.proof_of_work_bits = r.u32();
     const uint32_t width = r.u32(), log_q = r.u32();
-    if (!r.ok || len < 8 || fri.log_blowup > 16 || fri.log_final_poly_len > 31 || log_q > 8) return LSP_ERR_PARAM;
+    // the header comes from outside: hold it to the ranges the prover accepts (check_fri_config) BEFORE anything walks the
+    // shape it describes -- a stream promising 2^32 queries must cost nothing to refuse
+    if (!r.ok || len < 8 || fri.log_blowup > 16 || fri.log_final_poly_len > 31 || log_q > fri.log_blowup || fri.num_queries == 0 ||
+        fri.num_queries > 4096 || fri.proof_of_work_bits > 32 || width == 0 || width > (1u << 20))
+        return LSP_ERR_PARAM;
     uint64_t log_n64;
     memcpy(&log_n64, bytes + len - 8, 8);                        // degree_bits closes the stream: the shape depends on it
     if (log_n64 > 31) return LSP_ERR_PARAM;

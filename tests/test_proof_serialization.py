@@ -80,6 +80,20 @@ def test_malformed_streams_are_rejected(pkg, p2params):
             pkg.Proof.deserialize(bad)
 
 
+def test_absurd_headers_are_refused_at_once(pkg, p2params):
+    """A header that promises 2^32 queries (or a 2^32-column trace) must be refused before anything walks the shape it describes
+    (found by tools/serialize_asan_harness.cpp: the size pass used to iterate over the promised queries first)."""
+    import time
+    proof = port_proof(pkg, p2params, 3, 1, dict(log_blowup=1, log_final_poly_len=0, num_queries=2, proof_of_work_bits=0))
+    blob = proof.serialize()
+    for off, val in ((16, 0xFFFFFFFF), (16, 0), (24, 0xFFFFFFFF), (24, 0), (20, 33), (28, 9)):   # num_queries, width, pow bits, log_q
+        bad = blob[:off] + struct.pack("<I", val) + blob[off + 4:]
+        t0 = time.perf_counter()
+        with pytest.raises(pkg.BackendError):
+            pkg.Proof.deserialize(bad)
+        assert time.perf_counter() - t0 < 0.5
+
+
 @pytest.mark.gpu
 def test_a_deserialised_proof_verifies_on_the_device(pkg, gctx, p2params):
     fri_kw = dict(log_blowup=2, log_final_poly_len=1, num_queries=6, proof_of_work_bits=2)
