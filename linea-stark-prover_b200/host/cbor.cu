@@ -707,6 +707,7 @@ extern "C" int lsp_cbor_lookup_read_rows(const uint8_t* cbor, size_t len, size_t
     std::vector<Run> runs;
     if (!lookup_shape(cbor, len, s, &runs) || s.height() == 0) return LSP_ERR_PARAM;
     const size_t h = s.height() > min_rows ? s.height() : min_rows, stride = s.a_rows.size() + s.b_rows.size() * (s.b_rows[0].size() + 1) + 1;
+    if (h > SIZE_MAX / 32 / stride) return LSP_ERR_NOMEM;   // a target height whose buffer size would wrap
     uint8_t* out = static_cast<uint8_t*>(host_alloc(h * stride * 32));
     if (!out) return LSP_ERR_NOMEM;
     if (!fill_lookup(cbor, len, s, runs, out, h)) {
@@ -754,6 +755,7 @@ extern "C" int lsp_cbor_permutation_read_rows(const uint8_t* cbor, size_t len, s
     std::vector<Run> runs;
     if (!permutation_shape(cbor, len, s, &runs) || s.height() == 0) return LSP_ERR_PARAM;
     const size_t h = s.height() > min_rows ? s.height() : min_rows, nc = s.a_rows.size();
+    if (h > SIZE_MAX / 64 / nc) return LSP_ERR_NOMEM;       // a target height whose buffer size would wrap
     uint8_t* out = static_cast<uint8_t*>(host_alloc(h * 2 * nc * 32));
     if (!out) return LSP_ERR_NOMEM;
     if (!fill_permutation(cbor, len, s, runs, out, h)) {
