@@ -10,9 +10,9 @@ use lsp_b200_sys as sys;
 use p3_bls12_377_fr::Bls12_377Fr as Val;
 use p3_commit::{Mmcs, Pcs, TwoAdicMultiplicativeCoset};
 use p3_dft::TwoAdicSubgroupDft;
-use p3_field::{Field, TwoAdicField};
+use p3_field::{Field, FieldAlgebra, TwoAdicField};
 use p3_fri::{BatchOpening, CommitPhaseProofStep, FriConfig, FriProof, QueryProof};
-use p3_matrix::{bitrev::BitReversedMatrixView, dense::RowMajorMatrix, Dimensions, Matrix};
+use p3_matrix::{bitrev::{BitReversableMatrix, BitReversedMatrixView}, dense::RowMajorMatrix, Dimensions, Matrix};
 use p3_symmetric::{CryptographicHasher, Hash, Permutation};
 use p3_uni_stark::{Commitments, OpenedValues, Proof, StarkGenericConfig};
 
@@ -176,7 +176,7 @@ struct CfgStore { ids: Vec<Vec<u32>>, perms: Vec<sys::lsp_perm_air_cfg>, lookups
 /// `Vec<AirConfig>` (what `RawTrace::push_traces` returns, trace/src/lib.rs:62-92) -> the C structs, lookups first.
 fn c_configs(cfgs: &[AirConfig]) -> CfgStore {
     let mut s = CfgStore { ids: Vec::new(), perms: Vec::new(), lookups: Vec::new() };
-    let mut keep = |v: &[usize], s: &mut CfgStore| -> *const u32 { s.ids.push(v.iter().map(|&x| x as u32).collect()); s.ids.last().unwrap().as_ptr() };
+    let keep = |v: &[usize], s: &mut CfgStore| -> *const u32 { s.ids.push(v.iter().map(|&x| x as u32).collect()); s.ids.last().unwrap().as_ptr() };
     for c in cfgs {
         match c {
             AirConfig::Permutation(AirPermutationConfig { a_columns_ids, b_columns_ids, b_inverse_id, check_id }) => {
