@@ -30,12 +30,98 @@
 
 #include "../../include/lsp_b200.h"
 
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+#define LSP_CBOR_SIMD 1
+#endif
+
 namespace {
+
+#ifdef LSP_CBOR_SIMD
+// Tables for the vectorised element decoder, indexed by an 8-bit mask of value-carrying bytes: the PSHUFB control that packs
+// those bytes to the front of an 8-byte group, and the position of the k-th set bit.  (PEXT / PDEP would do both without
+// tables, but they are microcoded -- hundreds of cycles -- on some hosts; the tables cost 4 KB of L1 and are fast everywhere.)
+struct ElemTables {
+    uint64_t pack[256];
+    uint8_t kth[256][8];
+    ElemTables() {
+        for (unsigned m = 0; m < 256; m++) {
+            uint64_t ctl = 0;
+            unsigned k = 0;
+            for (unsigned i = 0; i < 8; i++)
+                if (m >> i & 1) {
+                    ctl |= uint64_t(i) << (8 * k);
+                    kth[m][k++] = uint8_t(i);
+                }
+            for (unsigned j = k; j < 8; j++) {
+                ctl |= uint64_t(0x80) << (8 * j);    // PSHUFB writes zero
+                kth[m][j] = 0;
+            }
+            pack[m] = ctl;
+        }
+    }
+};
+const ElemTables g_elem_tables;
+
+// The canonical element, 64 value-region bytes at a time (AVX2; chosen at run time, the scalar loop below is the
+// reference it is fuzzed against).  A value is one byte b < 0x18 or the pair `18 b`; which 0x18 bytes are MARKERS is a
+// parity question inside runs of 0x18 (`18 18` is the value 24: marker, payload) -- the first byte of a run is a marker,
+// then every second one.  With E = "byte == 0x18" and S = the run starts, adding the even-positioned starts to E clears
+// exactly the runs that begin on an even position (the carry ripples through the run and lands behind it), which tells the
+// two kinds of run apart; markers are the even positions of the first kind and the odd positions of the second.  Every
+// non-marker byte carries a value; the 32nd of them ends the element (per-byte popcounts, a multiply for their prefix sums,
+// one table look-up inside the group where the sum crosses 32); a non-marker byte that does not follow a marker must be
+// < 0x18; PSHUFB packs the value bytes eight input bytes at a time.
+__attribute__((target("avx2,popcnt"))) const uint8_t* fast_elem_simd(const uint8_t* p, uint8_t* dst) {
+    // the caller guarantees 66 readable bytes at p
+    if (p[0] != 0x98 || p[1] != 0x20) return nullptr;
+    const uint8_t* q = p + 2;
+    const __m256i lo = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(q));
+    const __m256i hi = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(q + 32));
+    const __m256i k18 = _mm256_set1_epi8(0x18), k19 = _mm256_set1_epi8(0x19);
+    const uint64_t E = uint64_t(uint32_t(_mm256_movemask_epi8(_mm256_cmpeq_epi8(lo, k18)))) |
+                       (uint64_t(uint32_t(_mm256_movemask_epi8(_mm256_cmpeq_epi8(hi, k18)))) << 32);
+    const uint64_t G = uint64_t(uint32_t(_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_max_epu8(lo, k19), lo)))) |   // byte >= 0x19
+                       (uint64_t(uint32_t(_mm256_movemask_epi8(_mm256_cmpeq_epi8(_mm256_max_epu8(hi, k19), hi)))) << 32);
+    const uint64_t EVEN = 0x5555555555555555ull;
+    const uint64_t S = E & ~(E << 1);
+    const uint64_t r_even = E & ~(E + (S & EVEN));              // the bytes of runs that start on an even position
+    const uint64_t M = (r_even & EVEN) | (E & ~r_even & ~EVEN);  // markers (never adjacent: at most 32 of the 64 bytes)
+    const uint64_t V = ~M;                                      // value bytes: one-byte values and marker payloads
+    uint64_t c = V - ((V >> 1) & EVEN);                         // popcount of every byte of V ...
+    c = (c & 0x3333333333333333ull) + ((c >> 2) & 0x3333333333333333ull);
+    c = (c + (c >> 4)) & 0x0f0f0f0f0f0f0f0full;
+    const uint64_t pre = c * 0x0101010101010101ull;             // ... and their inclusive prefix sums (<= 64: no carries)
+    const unsigned grp = unsigned(__builtin_ctzll(((pre | 0x8080808080808080ull) - 0x2020202020202020ull) & 0x8080808080808080ull)) >> 3;
+    const unsigned before = grp ? unsigned(pre >> (8 * grp - 8)) & 0xff : 0;       // value bytes in the groups before it (< 32)
+    const unsigned n = 8 * grp + g_elem_tables.kth[(V >> (8 * grp)) & 0xff][31 - before] + 1;   // up to and incl. the 32nd value byte
+    const uint64_t used = n == 64 ? ~0ull : (1ull << n) - 1;
+    if (G & V & ~(M << 1) & used) return nullptr;               // >= 0x19 where a one-byte value must stand: not this shape
+    if (dst) {
+        alignas(16) uint8_t tmp[48];
+        const uint64_t vu = V & used;
+        unsigned off = 0;
+        for (unsigned g = 0; g <= grp; g++) {
+            const unsigned m8 = unsigned(vu >> (8 * g)) & 0xff;
+            const __m128i word = _mm_loadl_epi64(reinterpret_cast<const __m128i*>(q + 8 * g));
+            const __m128i ctl = _mm_loadl_epi64(reinterpret_cast<const __m128i*>(&g_elem_tables.pack[m8]));
+            _mm_storel_epi64(reinterpret_cast<__m128i*>(tmp + off), _mm_shuffle_epi8(word, ctl));
+            off += unsigned(_mm_popcnt_u32(m8));
+        }
+        memcpy(dst, tmp, 32);
+    }
+    return q + n;
+}
+const bool g_cbor_simd = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt") && !getenv("LSP_CBOR_SCALAR");
+#endif
 
 // serde's canonical `[u8;32]`: array(32) head `98 20`, then 32 values, each one byte (< 24) or `18 b`.
 // Returns the position after the element, or nullptr when the bytes at p are anything else.
 inline const uint8_t* fast_elem(const uint8_t* p, const uint8_t* end, uint8_t* dst) {
     if (end - p < 34 || p[0] != 0x98 || p[1] != 0x20) return nullptr;
+#ifdef LSP_CBOR_SIMD
+    if (g_cbor_simd && end - p >= 66) return fast_elem_simd(p, dst);
+#endif
     const uint8_t* q = p + 2;
     unsigned bad = 0;
     if (end - p >= 66) {            // the longest element fits: no bounds checks inside

@@ -116,3 +116,61 @@ def test_mutated_lookup_files(pkg, monkeypatch, seed):
     assert _both(pkg, monkeypatch, blob, lookup=True) is not None
     for bad in _mutations(blob, rng, 150):
         _both(pkg, monkeypatch, bad, lookup=True)          # survive, and agree with itself
+
+
+# ---- the vectorised element decoder (cbor.cu: fast_elem_simd) against the byte-serial one and cbor2 ---------------
+_ADVERSARIAL = [0x00, 0x17, 0x18, 0x18, 0x18, 0x19, 0x20, 0x98, 0xff]
+
+
+def _element_cases(seed, n):
+    """Files of one column pair whose elements are full of 0x18 (marker == payload runs), plus damaged copies: bytes of the
+    element region overwritten from an alphabet that produces markers, 0x19.. heads and fake `98 20` pairs."""
+    rng = random.Random(seed)
+    cases = []
+    for _ in range(n):
+        rows = rng.choice([33, 34, 40])
+        col = [[rng.choice(_ADVERSARIAL) if rng.random() < 0.8 else rng.randrange(256) for _ in range(32)] for _ in range(rows)]
+        blob = bytearray(cbor2.dumps({"a": [col], "b": [col[::-1]], "name": "e"}))
+        if rng.random() < 0.7:
+            lo = blob.index(b"\x98\x20")
+            for _ in range(rng.randrange(1, 6)):
+                blob[rng.randrange(lo, len(blob) - 8)] = rng.choice(_ADVERSARIAL + [0x1a, 0x38, 0x58])
+        cases.append(bytes(blob))
+    return cases
+
+
+def _element_digest(pkg, cases):
+    import hashlib
+    out = []
+    for blob in cases:
+        got = _read(pkg, blob, lookup=False)
+        out.append(None if got is None else (got[0], hashlib.sha256(got[1].tobytes()).hexdigest()))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_vector_element_decoder_equals_scalar_and_cbor2(pkg, monkeypatch, seed):
+    import json
+    import os
+    import subprocess
+    import sys
+    cases = _element_cases(seed, 250)
+    accepted = 0
+    for blob in cases:
+        got, want = _both(pkg, monkeypatch, blob, lookup=False), _expected_permutation(blob)
+        if got is not None and want is not None and want[0] > 0:
+            assert got[0] == (want[0], want[1], want[2]) and np.array_equal(got[1], want[3])
+            accepted += 1
+        if want is not None and want[0] > 0 and len(cbor2.dumps(cbor2.loads(blob))) == len(blob):
+            assert got is not None
+    assert accepted >= 50
+    # the same files through the byte-serial decoder (a fresh process: the choice is made when the library loads)
+    monkeypatch.setenv("LSP_CBOR_THREADS", "1")
+    monkeypatch.delenv("LSP_CBOR_PRESCAN_MIN", raising=False)
+    here = _element_digest(pkg, cases)
+    code = ("import json, sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import __graft_entry__ as g; import test_cbor_fuzz as t; "
+            "print(json.dumps(t._element_digest(g.load_package(), t._element_cases(%d, 250))))") % (
+        os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), seed)
+    env = dict(os.environ, LSP_CBOR_SCALAR="1", LSP_CBOR_THREADS="1")
+    scalar = json.loads(subprocess.run([sys.executable, "-c", code], env=env, check=True, capture_output=True, text=True).stdout.splitlines()[-1])
+    assert [None if d is None else [list(d[0]), d[1]] for d in here] == scalar
