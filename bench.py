@@ -225,21 +225,34 @@ class CpuProver:
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    t_start = time.perf_counter()
     cpu = CpuProver(args)
-    vals, words = [], None
-    for i in range(args.warmup + args.steps):
+    # Every step is one full prove of the configured trace (26 s on 16 host threads at the default size).  The driver's
+    # clock around this arm is finite (870 s per N in round 1): once the next prove would not fit in LSP_REF_BUDGET_S the
+    # loop stops -- warm-up first, timed steps after -- and the line reports the steps it did time (`steps` / `steps_requested`).
+    budget = float(os.environ.get("LSP_REF_BUDGET_S", "780"))
+    vals, words, warmup, warm_done, dt = [], None, args.warmup, 0, None
+    while len(vals) < args.steps:
+        if dt is not None:
+            left = budget - (time.perf_counter() - t_start)
+            if vals and left < 1.05 * dt:
+                break                                    # the next timed prove would not fit
+            if not vals and warm_done < warmup and left < 1.05 * dt * (warmup - warm_done + args.steps):
+                warmup = warm_done                       # no room for the whole warm-up AND every timed step: start timing now
         dt, words = cpu.prove()
-        if i >= args.warmup:
+        if warm_done < warmup:
+            warm_done += 1
+        else:
             vals.append(dt)
     assert cpu.verify(words), "the CPU port's verifier rejected the CPU port's proof"
     v = float(np.mean(vals))
     tp, qp, fp = perm_counts(args.log_n, cpu.w, args.log_blowup, 2, 0)
-    sample = (f"C port of the reference prover (oracle/c, OpenMP): {args.steps} full proves of the 2^{args.log_n}-row, "
+    sample = (f"C port of the reference prover (oracle/c, OpenMP): {len(vals)} full proves of the 2^{args.log_n}-row, "
               f"{cpu.w}-column trace named in config, {cpu.threads} threads, {(tp + qp + fp) / v:.3g} Poseidon2 perms/s; "
               f"nothing sampled")
     print_json({
-        "impl": "reference", "metric": "prove_seconds", "value": v, "unit": "s", "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
+        "impl": "reference", "metric": "prove_seconds", "value": v, "unit": "s", "n_gpus": world, "steps": len(vals),
+        "steps_requested": args.steps, "warmup": warm_done, "warmup_requested": args.warmup, "ms_per_step": v * 1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "u256 (BLS12-377 Fr, Montgomery 4x64-bit)", "data": "synthetic",
         "config": workload_config(args, world),   # the workload this arm ran: rows/width below are what was proved
         "cpu_baseline": {"value": v, "unit": "s", "cores": cpu.threads, "kind": "port", "sample": sample},
