@@ -50,7 +50,7 @@ impl GpuCtx {
     /// run the host's own `Perm`, `Hash`, `Dft` beside the device once per process and abort on
     /// the first mismatch -- this is how the fork-only details (S-box degree, matrices, generators) get caught.
     pub fn parity_probe<P: Permutation<[Val; 3]>, H: CryptographicHasher<Val, [Val; 1]>, D: TwoAdicSubgroupDft<Val>>(&self, perm: &P, hash: &H, dft: &D) {
-        let x: Vec<Val> = (1..=24u64).map(|i| Val::from_canonical_u64(i * 0x9e3779b97f4a7c15 % 0xffff_fffb)).collect();
+        let x: Vec<Val> = (1..=24u64).map(|i| Val::from_canonical_u64(i.wrapping_mul(0x9e3779b97f4a7c15) % 0xffff_fffb)).collect();
         let mut got = zeros(3);
         self.must(unsafe { sys::lsp_poseidon2_permute(self.raw, limbs(&x[..3]), limbs_mut(&mut got), 1) });
         assert_eq!(perm.permute([x[0], x[1], x[2]]).to_vec(), got, "Poseidon2 permutation differs: S-box degree / linear layers?");
